@@ -1,0 +1,49 @@
+// vqb200 -- ABI plumbing: version, thread-local error string, launch counter.
+#include <stdarg.h>
+#include <atomic>
+#include "common.cuh"
+
+namespace vqb200 {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return (int)e;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached = n; cached_dev = dev;
+  }
+  return cached;
+}
+
+}  // namespace vqb200
+
+extern "C" {
+int vqb200_abi_version(void) { return VQB200_ABI_VERSION; }
+const char* vqb200_last_error_string(void) { return vqb200::g_err; }
+int64_t vqb200_launch_count(void) { return (int64_t)vqb200::g_launches.load(); }
+}

@@ -1,0 +1,50 @@
+// vqb200 K1 dispatch: picks the tcgen05 filter+rerank kernel (assign_tc.cu) when the shape is
+// eligible and falls back to the exact CUDA-core kernel (assign_simt.cu) otherwise.
+#include "common.cuh"
+#include "codebook.cuh"
+
+namespace vqb200 {
+int launch_assign_simt(const ZView& z, const float* E, const float* ee, int K, int D,
+                       int32_t* idx, float* best, const int32_t* row_list, const int32_t* row_count,
+                       long long max_rows, cudaStream_t stream);
+bool assign_tc_eligible(const ZView& z, int K, int D);
+int launch_assign_tc(const ZView& z, const float* E, const float* ee, const void* image, const float* info,
+                     int K, int D, int32_t* idx, float* best, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream);
+size_t assign_tc_workspace_bytes(long long N);
+}  // namespace vqb200
+
+using namespace vqb200;
+
+extern "C" {
+
+size_t vqb200_assign_workspace_bytes(int64_t N) { return assign_tc_workspace_bytes(N); }
+
+int vqb200_vq_assign(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,
+                     const float* E, const float* ee, const void* image, const float* info, int64_t K,
+                     int32_t* idx, float* best, void* workspace, size_t workspace_bytes, int algo,
+                     vqb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VQ_CHECK_ARG(z && E && ee && idx, VQB200_EINVAL, "vq_assign: null pointer");
+  VQ_CHECK_ARG(B >= 0 && C > 0 && T > 0 && K > 0 && K < (1LL << 30) && C < (1 << 16), VQB200_ESHAPE,
+               "vq_assign: bad shape B=%lld C=%lld T=%lld K=%lld", (long long)B, (long long)C, (long long)T, (long long)K);
+  VQ_CHECK_ARG(B * T < (1LL << 31), VQB200_ESHAPE, "vq_assign: N=%lld exceeds int32 row ids", (long long)(B * T));
+  if (B * T == 0) return VQB200_OK;
+  const ZView zv = make_zview(z, B, C, T, sB, sC, sT);
+  const int D = (int)C;
+  bool use_tc = false;
+  if (algo == VQB200_ASSIGN_TC) {
+    VQ_CHECK_ARG(image && info && workspace, VQB200_EINVAL, "vq_assign(TC): image, info and workspace are required");
+    VQ_CHECK_ARG(assign_tc_eligible(zv, (int)K, D), VQB200_EUNSUPPORTED, "vq_assign(TC): shape K=%lld D=%d not eligible", (long long)K, D);
+    use_tc = true;
+  } else if (algo == VQB200_ASSIGN_AUTO) {
+    use_tc = image && info && workspace && assign_tc_eligible(zv, (int)K, D) &&
+             workspace_bytes >= assign_tc_workspace_bytes(zv.N) && zv.N >= 2048;
+  } else {
+    VQ_CHECK_ARG(algo == VQB200_ASSIGN_SIMT, VQB200_EINVAL, "vq_assign: unknown algo %d", algo);
+  }
+  if (use_tc) return launch_assign_tc(zv, E, ee, image, info, (int)K, D, idx, best, workspace, workspace_bytes, stream);
+  return launch_assign_simt(zv, E, ee, (int)K, D, idx, best, nullptr, nullptr, zv.N, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+// vqb200 K5: FSQ / LFQ elementwise stages with on-device unique-code counting.
+// Replaces models/vqvae.py:127-147,152-154 (FSQ) and :171-191 (LFQ) of the reference, including the
+// host-synchronising torch.unique().numel() (:142, :186), which becomes a bitmap + hash-set insert
+// and a last-CTA finalize: no host read-back, CUDA-graph capturable.
+#include "common.cuh"
+#include <limits.h>
+
+namespace vqb200 {
+
+// ---- unique-code workspace ----------------------------------------------------------------
+//   [0]   u32 unique count      [4] u32 ticket      [8] u32 hash overflow flag
+//   [16]  f64 entropy sum (LFQ)
+//   [64 .. 64+UNIQ_BITMAP_BYTES)           bitmap for codes in [-UNIQ_HALF, UNIQ_HALF)
+//   [.. + UNIQ_HASH_SLOTS*8)               open-addressing set for codes outside the window (0 = empty)
+constexpr long long UNIQ_HALF = 1LL << 20;
+constexpr size_t UNIQ_BITMAP_BYTES = (size_t)(2 * UNIQ_HALF) / 8;      // 256 KiB
+constexpr int UNIQ_HASH_SLOTS = 1 << 16;
+constexpr size_t UNIQ_WS_BYTES = 64 + UNIQ_BITMAP_BYTES + (size_t)UNIQ_HASH_SLOTS * 8;
+
+struct UniqWs {
+  unsigned* count; unsigned* ticket; unsigned* overflow; double* ent;
+  unsigned* bitmap; unsigned long long* hash;
+  __host__ __device__ explicit UniqWs(void* ws) {
+    unsigned char* b = reinterpret_cast<unsigned char*>(ws);
+    count = reinterpret_cast<unsigned*>(b); ticket = count + 1; overflow = count + 2;
+    ent = reinterpret_cast<double*>(b + 16);
+    bitmap = reinterpret_cast<unsigned*>(b + 64);
+    hash = reinterpret_cast<unsigned long long*>(b + 64 + UNIQ_BITMAP_BYTES);
+  }
+};
+
+__device__ __forceinline__ void unique_insert(const UniqWs& w, long long code) {
+  if (code >= -UNIQ_HALF && code < UNIQ_HALF) {
+    const unsigned bit = (unsigned)(code + UNIQ_HALF);
+    unsigned* word = w.bitmap + (bit >> 5);
+    const unsigned m = 1u << (bit & 31);
+    if (!(*reinterpret_cast<volatile unsigned*>(word) & m)) {      // skip the atomic once the bit is visible
+      const unsigned old = atomicOr(word, m);
+      if (!(old & m)) atomicAdd(w.count, 1u);
+    }
+  } else {
+    const unsigned long long key = (unsigned long long)code;      // never 0: 0 lies inside the window
+    unsigned long long h = key * 0x9E3779B97F4A7C15ull;
+    unsigned slot = (unsigned)(h >> 40) & (UNIQ_HASH_SLOTS - 1);
+    for (int probe = 0; probe < UNIQ_HASH_SLOTS; ++probe) {
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(w.hash + slot);
+      if (cur == key) return;
+      if (cur == 0ull) {
+        cur = atomicCAS(w.hash + slot, 0ull, key);
+        if (cur == 0ull) { atomicAdd(w.count, 1u); return; }
+        if (cur == key) return;
+      }
+      slot = (slot + 1) & (UNIQ_HASH_SLOTS - 1);
+    }
+    atomicExch(w.overflow, 1u);                                     // set is full: metrics become NaN
+  }
+}
+
+// returns true in exactly one thread of the last CTA to finish
+__device__ __forceinline__ bool last_block_done(const UniqWs& w) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(w.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  return s_last && threadIdx.x == 0;
+}
+
+__device__ __forceinline__ long long trunc_to_i64(float s) {
+  // x86 cvttss2si semantics of torch's CPU .long(): NaN / out of range -> INT64_MIN
+  if (!(fabsf(s) < 9.2233720368547758e18f)) return LLONG_MIN;
+  return (long long)s;
+}
+
+constexpr int FSQ_MAX_D = 16;
+
+__global__ void __launch_bounds__(256)
+fsq_forward_kernel(const float* __restrict__ z_e, long long B, int d, int T, const int32_t* __restrict__ basis,
+                   double codebook_size, float* __restrict__ z_hard, long long* __restrict__ idx,
+                   void* ws, float* __restrict__ out2) {
+  const UniqWs w(ws);
+  float fb[FSQ_MAX_D];
+#pragma unroll
+  for (int i = 0; i < FSQ_MAX_D; ++i) fb[i] = (i < d) ? (float)__ldg(basis + i) : 0.f;
+  const long long N = B * T, dT = (long long)d * T;
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    const long long b = n / T; const int t = (int)(n - b * T);
+    const long long base = b * dT + t;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < FSQ_MAX_D; ++i) {
+      if (i < d) {
+        const float z = __ldg(z_e + base + (long long)i * T);
+        const float zh = __fadd_rn(z, __fsub_rn(rintf(z), z));     // z + (round(z) - z), half-to-even
+        z_hard[base + (long long)i * T] = zh;
+        const float p = __fmul_rn(zh, fb[i]);
+        s = (i == 0) ? p : __fadd_rn(s, p);
+      }
+    }
+    const long long code = trunc_to_i64(s);
+    idx[n] = code;
+    unique_insert(w, code);
+  }
+  if (last_block_done(w)) {
+    const unsigned u = atomicAdd(w.count, 0u);
+    const bool ovf = atomicAdd(w.overflow, 0u) != 0u;
+    out2[0] = ovf ? NAN : (float)u;
+    out2[1] = ovf ? NAN : (float)(1.0 - (double)u / codebook_size);
+  }
+}
+
+constexpr int LFQ_MAX_D = 32;
+
+__global__ void __launch_bounds__(256)
+lfq_forward_kernel(const float* __restrict__ z_e, long long B, int d, int T, float weight,
+                   float* __restrict__ z_q, long long* __restrict__ idx, void* ws, float* __restrict__ out3) {
+  const UniqWs w(ws);
+  const long long N = B * T, dT = (long long)d * T;
+  float part = 0.f;
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (long long)gridDim.x * blockDim.x) {
+    const long long b = n / T; const int t = (int)(n - b * T);
+    const long long base = b * dT + t;
+    long long code = 0;
+    for (int i = 0; i < d; ++i) {
+      const float z = __ldg(z_e + base + (long long)i * T);
+      const float sgn = (z > 0.f) ? 1.f : -1.f;
+      const float zq = __fadd_rn(z, __fsub_rn(sgn, z));
+      z_q[base + (long long)i * T] = zq;
+      if (zq > 0.f) code |= (1LL << i);
+      const float p = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-z)));
+      const float q = __fsub_rn(1.f, p);
+      const float ent = -__fadd_rn(__fmul_rn(p, logf(__fadd_rn(p, 1e-6f))), __fmul_rn(q, logf(__fadd_rn(q, 1e-6f))));
+      part += ent;
+    }
+    idx[n] = code;
+    unique_insert(w, code);
+  }
+  __shared__ double red[8];
+  double p = warp_sum((double)part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = p;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < 8 ? red[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(w.ent, v);
+  }
+  if (last_block_done(w)) {
+    const unsigned u = atomicAdd(w.count, 0u);
+    const bool ovf = atomicAdd(w.overflow, 0u) != 0u;
+    const double sum = atomicAdd(w.ent, 0.0);
+    const float mean = (float)(sum / ((double)N * d));
+    out3[0] = __fmul_rn(-mean, weight);
+    out3[1] = ovf ? NAN : (float)u;
+    out3[2] = ovf ? NAN : (float)(1.0 - (double)u / exp2((double)d));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+lfq_backward_kernel(const float* __restrict__ z_e, const float* __restrict__ g_zq, const float* __restrict__ g_loss,
+                    long long numel, float weight, float* __restrict__ g_ze) {
+  const float scale = (g_loss ? __ldg(g_loss) : 1.f) * (-weight / (float)numel);
+  const float dl = 1e-6f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (long long)gridDim.x * blockDim.x) {
+    const float z = __ldg(z_e + i);
+    const float p = 1.f / (1.f + expf(-z));
+    const float q = 1.f - p;
+    const float dH = -(logf(p + dl) + p / (p + dl) - logf(q + dl) - q / (q + dl));
+    const float gin = g_zq ? __ldg(g_zq + i) : 0.f;
+    g_ze[i] = fmaf(scale * dH, p * q, gin);
+  }
+}
+
+}  // namespace vqb200
+
+using namespace vqb200;
+
+extern "C" {
+
+size_t vqb200_unique_workspace_bytes(void) { return UNIQ_WS_BYTES; }
+
+int vqb200_fsq_forward(const float* z_e, int64_t B, int64_t d, int64_t T, const int32_t* basis,
+                       int64_t codebook_size, float* z_hard, int64_t* idx, void* workspace, float* out2,
+                       vqb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VQ_CHECK_ARG(z_e && basis && z_hard && idx && workspace && out2, VQB200_EINVAL, "fsq_forward: null pointer");
+  VQ_CHECK_ARG(B >= 0 && T > 0 && d > 0 && d <= FSQ_MAX_D, VQB200_ESHAPE, "fsq_forward: unsupported d=%lld (max %d)", (long long)d, FSQ_MAX_D);
+  VQ_CHECK_ARG(codebook_size > 0, VQB200_EINVAL, "fsq_forward: codebook_size must be positive");
+  VQ_CUDA(cudaMemsetAsync(workspace, 0, UNIQ_WS_BYTES, stream));
+  const long long N = B * T;
+  const int grid = grid_for(N, 256, sm_count() * 8);
+  fsq_forward_kernel<<<grid, 256, 0, stream>>>(z_e, B, (int)d, (int)T, basis, (double)codebook_size, z_hard,
+                                               (long long*)idx, workspace, out2);
+  VQ_LAUNCH_CHECK("fsq_forward_kernel");
+  return VQB200_OK;
+}
+
+int vqb200_lfq_forward(const float* z_e, int64_t B, int64_t d, int64_t T, float entropy_loss_weight,
+                       float* z_q, int64_t* idx, void* workspace, float* out3, vqb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VQ_CHECK_ARG(z_e && z_q && idx && workspace && out3, VQB200_EINVAL, "lfq_forward: null pointer");
+  VQ_CHECK_ARG(B > 0 && T > 0 && d > 0 && d <= LFQ_MAX_D, VQB200_ESHAPE, "lfq_forward: unsupported shape d=%lld (max %d, B>0)", (long long)d, LFQ_MAX_D);
+  VQ_CUDA(cudaMemsetAsync(workspace, 0, UNIQ_WS_BYTES, stream));
+  const long long N = B * T;
+  const int grid = grid_for(N, 256, sm_count() * 8);
+  lfq_forward_kernel<<<grid, 256, 0, stream>>>(z_e, B, (int)d, (int)T, entropy_loss_weight, z_q, (long long*)idx,
+                                               workspace, out3);
+  VQ_LAUNCH_CHECK("lfq_forward_kernel");
+  return VQB200_OK;
+}
+
+int vqb200_lfq_backward(const float* z_e, const float* g_zq, const float* g_loss, int64_t numel,
+                        float entropy_loss_weight, float* g_ze, vqb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VQ_CHECK_ARG(z_e && g_ze, VQB200_EINVAL, "lfq_backward: null pointer");
+  if (numel <= 0) return VQB200_OK;
+  lfq_backward_kernel<<<grid_for(numel, 256 * 4, sm_count() * 8), 256, 0, stream>>>(z_e, g_zq, g_loss, numel,
+                                                                                  entropy_loss_weight, g_ze);
+  VQ_LAUNCH_CHECK("lfq_backward_kernel");
+  return VQB200_OK;
+}
+
+}  // extern "C"

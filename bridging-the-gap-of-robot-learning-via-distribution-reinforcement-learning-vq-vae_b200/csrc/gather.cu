@@ -1,0 +1,152 @@
+// vqb200 K2 / K2b / metrics: codeword gather + straight-through + loss partial sums, input
+// gradient, loss / perplexity / dead-code-ratio as device scalars.
+// Replaces models/vqvae.py:52-76 of the reference and the autograd backward of :52-63.
+#include "common.cuh"
+
+namespace vqb200 {
+
+struct Decomp { long long b; int c, t; };
+
+__device__ __forceinline__ Decomp decomp(long long i, int C, int T, long long CT) {
+  Decomp d;
+  d.b = i / CT;
+  const int rem = (int)(i - d.b * CT);
+  d.c = rem / T;
+  d.t = rem - d.c * T;
+  return d;
+}
+
+// out[b,c,t] = x + (E[idx[b,t]][c] - x); sse += (q-x)^2; optional residual / running RVQ sum.
+__global__ void __launch_bounds__(256)
+gather_st_kernel(ZView z, const float* __restrict__ E, const int32_t* __restrict__ idx, int K,
+                 float* __restrict__ out, float* __restrict__ residual, float* __restrict__ accum,
+                 int accum_init, double* __restrict__ sse) {
+  const int C = (int)z.C, T = (int)z.T;
+  const long long CT = (long long)C * T, total = z.B * CT;
+  float part = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const Decomp d = decomp(i, C, T, CT);
+    const float x = __ldg(z.p + d.b * z.sB + (long long)d.c * z.sC + (long long)d.t * z.sT);
+    int k = __ldg(idx + d.b * T + d.t);
+    k = min(max(k, 0), K - 1);
+    const float q = __ldg(E + (size_t)k * C + d.c);
+    const float diff = __fsub_rn(q, x);
+    const float st = __fadd_rn(x, diff);
+    part = fmaf(diff, diff, part);
+    if (out) out[i] = st;
+    if (residual) residual[i] = __fsub_rn(x, st);
+    if (accum) accum[i] = __fadd_rn(accum_init ? accum[i] : 0.f, st);
+  }
+  __shared__ double red[8];
+  double p = warp_sum((double)part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = p;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < 8 ? red[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0 && v != 0.0) atomicAdd(sse, v);
+  }
+}
+
+// gz[b,c,t] = g[b,c,t] + g_loss*coef*(x - E[idx][c])
+__global__ void __launch_bounds__(256)
+backward_input_kernel(const float* __restrict__ g, long long gsB, long long gsC, long long gsT,
+                      ZView z, const float* __restrict__ E, const int32_t* __restrict__ idx, int K,
+                      const float* __restrict__ g_loss, float coef, float* __restrict__ gz) {
+  const int C = (int)z.C, T = (int)z.T;
+  const long long CT = (long long)C * T, total = z.B * CT;
+  const float s = __fmul_rn(g_loss ? __ldg(g_loss) : 1.0f, coef);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const Decomp d = decomp(i, C, T, CT);
+    const float x = __ldg(z.p + d.b * z.sB + (long long)d.c * z.sC + (long long)d.t * z.sT);
+    int k = __ldg(idx + d.b * T + d.t);
+    k = min(max(k, 0), K - 1);
+    const float q = __ldg(E + (size_t)k * C + d.c);
+    const float gv = g ? __ldg(g + d.b * gsB + (long long)d.c * gsC + (long long)d.t * gsT) : 0.f;
+    gz[i] = fmaf(s, __fsub_rn(x, q), gv);
+  }
+}
+
+// loss / perplexity / dcr (one CTA)
+__global__ void __launch_bounds__(1024)
+metrics_kernel(const float* __restrict__ cnt, int K, float Nf, const double* __restrict__ sse, double numel,
+               float commitment, int use_ema, float* __restrict__ out3) {
+  __shared__ double red_s[32];
+  __shared__ int red_a[32];
+  double s = 0.0; int active = 0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float c = cnt[k];
+    const float p = __fdiv_rn(c, Nf);
+    s += (double)__fmul_rn(p, logf(__fadd_rn(p, 1e-10f)));
+    active += (c > 0.f);
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) active += __shfl_xor_sync(0xffffffffu, active, o);
+  if ((threadIdx.x & 31) == 0) { red_s[threadIdx.x >> 5] = s; red_a[threadIdx.x >> 5] = active; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = red_s[threadIdx.x]; int a = red_a[threadIdx.x];
+    v = warp_sum(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (threadIdx.x == 0) {
+      if (sse) {
+        const float mse = (float)(*sse / numel);
+        out3[0] = use_ema ? __fmul_rn(commitment, mse) : __fadd_rn(mse, __fmul_rn(commitment, mse));
+      }
+      out3[1] = expf(-(float)v);
+      out3[2] = __fsub_rn(1.0f, __fdiv_rn((float)a, (float)K));
+    }
+  }
+}
+
+}  // namespace vqb200
+
+using namespace vqb200;
+
+extern "C" {
+
+int vqb200_vq_gather_st(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,
+                        const float* E, const int32_t* idx, int64_t K, float* out, float* residual,
+                        float* accum, int accum_init, double* sse, vqb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VQ_CHECK_ARG(z && E && idx && sse, VQB200_EINVAL, "vq_gather_st: null pointer");
+  VQ_CHECK_ARG(B >= 0 && C > 0 && T > 0 && K > 0 && C * T < (1LL << 31), VQB200_ESHAPE, "vq_gather_st: bad shape");
+  VQ_CUDA(cudaMemsetAsync(sse, 0, sizeof(double), stream));
+  const long long total = B * C * T;
+  if (total == 0) return VQB200_OK;
+  const ZView zv = make_zview(z, B, C, T, sB, sC, sT);
+  gather_st_kernel<<<grid_for(total, 256 * 4, sm_count() * 8), 256, 0, stream>>>(zv, E, idx, (int)K, out, residual,
+                                                                               accum, accum_init, sse);
+  VQ_LAUNCH_CHECK("gather_st_kernel");
+  return VQB200_OK;
+}
+
+int vqb200_vq_metrics(const float* cnt, int64_t K, int64_t N, const double* sse, int64_t numel,
+                      float commitment_cost, int use_ema, float* out3, vqb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VQ_CHECK_ARG(cnt && out3, VQB200_EINVAL, "vq_metrics: null pointer");
+  VQ_CHECK_ARG(K > 0 && N > 0, VQB200_ESHAPE, "vq_metrics: bad shape");
+  metrics_kernel<<<1, 1024, 0, stream>>>(cnt, (int)K, (float)N, sse, (double)numel, commitment_cost, use_ema, out3);
+  VQ_LAUNCH_CHECK("metrics_kernel");
+  return VQB200_OK;
+}
+
+int vqb200_vq_backward_input(const float* g, int64_t gsB, int64_t gsC, int64_t gsT,
+                             const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,
+                             const float* E, const int32_t* idx, int64_t K, const float* g_loss, float coef,
+                             float* gz, vqb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VQ_CHECK_ARG(z && E && idx && gz, VQB200_EINVAL, "vq_backward_input: null pointer");
+  VQ_CHECK_ARG(B >= 0 && C > 0 && T > 0 && K > 0 && C * T < (1LL << 31), VQB200_ESHAPE, "vq_backward_input: bad shape");
+  const long long total = B * C * T;
+  if (total == 0) return VQB200_OK;
+  const ZView zv = make_zview(z, B, C, T, sB, sC, sT);
+  backward_input_kernel<<<grid_for(total, 256 * 4, sm_count() * 8), 256, 0, stream>>>(g, gsB, gsC, gsT, zv, E, idx,
+                                                                                    (int)K, g_loss, coef, gz);
+  VQ_LAUNCH_CHECK("backward_input_kernel");
+  return VQB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+/*
+ * vqb200 -- C ABI of the B200-native vector-quantization engine.
+ *
+ * Drop-in boundary for the quantizer layer of the reference VQ-VAE retargeter.  The reference
+ * has no FFI of its own: its boundary is the Python nn.Module contract of
+ *   models/vqvae.py:10-259   (VectorQuantizer / ResidualVQ / FSQ / LFQ / HybridVQ / IdentityVQ)
+ * consumed at models/vqvae.py:540-560,588,605.  Each entry point below replaces the ATen ops the
+ * cited reference lines issue; the Python glue (package `vqb200`, drop-in `models/vqvae.py`)
+ * binds them with ctypes and re-creates the module contract on top.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer owned by the caller (torch);
+ *     the library never allocates or frees persistent device memory;
+ *   - z tensors are fp32 [B, C, T] addressed by ELEMENT strides (sB, sC, sT); vector n = b*T + t
+ *     has component k at z[b*sB + k*sC + t*sT]  (covers the contiguous channel-major layout and
+ *     the permuted T'=1 view the transformer encoder emits, models/vqvae.py:458-463);
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t); no host synchronisation,
+ *     no host read-back: every call is CUDA-graph capturable;
+ *   - return value: 0 = success, < 0 = VQB200_E* argument error, > 0 = cudaError_t;
+ *     vqb200_last_error_string() describes the last failure on the calling thread;
+ *   - there is no CPU fallback.
+ */
+#ifndef VQB200_H_
+#define VQB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQB200_ABI_VERSION 1
+
+#define VQB200_OK            0
+#define VQB200_EINVAL       -1   /* null pointer / non-positive size                        */
+#define VQB200_ESHAPE       -2   /* unsupported shape (e.g. C != D, D too large for smem)   */
+#define VQB200_EALIGN       -3   /* pointer not aligned as documented                       */
+#define VQB200_EUNSUPPORTED -4   /* configuration not built (e.g. tensor-core path, D%64)   */
+#define VQB200_EWORKSPACE   -5   /* workspace too small                                     */
+
+typedef void* vqb200_stream_t;   /* cudaStream_t */
+
+/* assignment algorithm selector for vqb200_vq_assign */
+#define VQB200_ASSIGN_AUTO  0    /* tcgen05 filter + exact rerank when eligible, else SIMT  */
+#define VQB200_ASSIGN_SIMT  1    /* exact fp32 CUDA-core path                               */
+#define VQB200_ASSIGN_TC    2    /* force the tcgen05 path (error if not eligible)          */
+
+int         vqb200_abi_version(void);
+const char* vqb200_last_error_string(void);
+/* number of kernels this library has launched from the calling process (bench.py's gpu_launches) */
+int64_t     vqb200_launch_count(void);
+
+/* ---- codebook-derived state ---------------------------------------------------------------
+ * |E_k|^2 (replaces torch.sum(weight**2, dim=1), models/vqvae.py:35) and the bf16 tile image the
+ * tcgen05 assignment kernel streams with bulk-TMA.  `image` may be NULL (SIMT only).
+ * image size in bytes: vqb200_codebook_image_bytes(K, D).  info[0..3] (device, 4 floats):
+ * {max_k |E_k|, nonfinite flag, reserved, reserved}. */
+size_t vqb200_codebook_image_bytes(int64_t K, int64_t D);
+int vqb200_codebook_prepare(const float* E, int64_t K, int64_t D,
+                            float* ee, void* image, float* info, vqb200_stream_t stream);
+
+/* ---- K1: fused distance + argmin ------------------- models/vqvae.py:30-38 (rows a2-a4) ----
+ * idx[n] = first index of min_k fl(fl(|x_n|^2 + |E_k|^2) - 2 x_n.E_k); NaN distance wins.
+ * Never materialises the N x K matrix.  idx: int32 [B*T].  best (optional, may be NULL): the
+ * winning fp32 distance per row.  workspace: vqb200_assign_workspace_bytes(N) bytes
+ * (may be NULL for the SIMT algorithm). */
+size_t vqb200_assign_workspace_bytes(int64_t N);
+int vqb200_vq_assign(const float* z, int64_t B, int64_t C, int64_t T,
+                     int64_t sB, int64_t sC, int64_t sT,
+                     const float* E, const float* ee, const void* image, const float* info,
+                     int64_t K, int32_t* idx, float* best,
+                     void* workspace, size_t workspace_bytes, int algo, vqb200_stream_t stream);
+
+/* ---- K3a: EMA statistics ------------------------------ models/vqvae.py:44-45 (row a5) -----
+ * stats = [dw (K*D) | cnt (K)] fp32, zeroed by this call then filled:
+ *   cnt[k] = #{n: idx_n = k}  (== encodings.sum(0)),  dw[k,:] = sum_{idx_n=k} x_n (== one_hot^T @ x).
+ * mode 0: as above.  mode 1 (standard-VQ codebook gradient, row a11): dw[k,:] = sum (E[k,:] - x_n).
+ * This buffer is what data-parallel ranks all-reduce. */
+int vqb200_ema_accumulate(const float* z, int64_t B, int64_t C, int64_t T,
+                          int64_t sB, int64_t sC, int64_t sT,
+                          const int32_t* idx, const float* E, int64_t K,
+                          float* stats, int mode, vqb200_stream_t stream);
+
+/* ---- K3b: EMA finalize -------------------------------- models/vqvae.py:46-50 (row a5) -----
+ * cs <- decay*cs + (1-decay)*cnt; w <- decay*w + (1-decay)*dw; n = sum(cs);
+ * E <- w / ((cs+eps)/(n+K*eps)*n)  in place; refreshes ee / image / info like codebook_prepare.
+ * decay / eps are the Python doubles of the reference (0.99, 1e-5); the kernels use
+ * (float)decay, (float)(1-decay), (float)eps and (float)(K*eps) exactly as torch does when it
+ * mixes Python scalars with fp32 tensors.  scratch: >= (K+8) floats. */
+int vqb200_ema_finalize(const float* stats, float* ema_cluster_size, float* ema_w, float* E,
+                        int64_t K, int64_t D, double decay, double eps,
+                        float* ee, void* image, float* info, float* scratch,
+                        vqb200_stream_t stream);
+
+/* ---- code histogram only (eval / non-EMA) --------------- models/vqvae.py:66,71 (row a9) --- */
+int vqb200_vq_histogram(const int32_t* idx, int64_t N, int64_t K, float* cnt, vqb200_stream_t stream);
+
+/* ---- K2: gather + straight-through + loss partial ----- models/vqvae.py:52-63,76 (a6-a8,a10)
+ * out[b,c,t] = x + (E[idx][c] - x)  written contiguous [B,C,T]; *sse += sum (E[idx][c]-x)^2
+ * (fp64 accumulator, zeroed by this call).
+ * residual (optional): residual[b,c,t] = x - out[b,c,t]  (ResidualVQ, models/vqvae.py:96).
+ * accum (optional):    accum[b,c,t]  = (accum_init ? accum : 0) + out  (models/vqvae.py:97). */
+int vqb200_vq_gather_st(const float* z, int64_t B, int64_t C, int64_t T,
+                        int64_t sB, int64_t sC, int64_t sT,
+                        const float* E, const int32_t* idx, int64_t K,
+                        float* out, float* residual, float* accum, int accum_init,
+                        double* sse, vqb200_stream_t stream);
+
+/* ---- loss + metrics as device scalars ----------------- models/vqvae.py:55-61,66-74 (a7,a9) -
+ * out3 = {loss, perplexity, dcr}.  loss = c*mse (EMA) or mse + c*mse (standard), mse = sse/numel;
+ * perplexity = exp(-sum p log(p+1e-10)), p = cnt/N; dcr = 1 - #{cnt>0}/K. */
+int vqb200_vq_metrics(const float* cnt, int64_t K, int64_t N, const double* sse, int64_t numel,
+                      float commitment_cost, int use_ema, float* out3, vqb200_stream_t stream);
+
+/* ---- K2b: input gradient ------------------------------------------------- (row a11) --------
+ * gz[b,c,t] = g[b,c,t] + g_loss[0]*coef*(x - E[idx][c]),  coef = c*2/(N*D).  g is addressed with
+ * its own element strides; gz is written contiguous [B,C,T].  g may be NULL (treated as 0);
+ * g_loss is a device scalar (NULL = 1). */
+int vqb200_vq_backward_input(const float* g, int64_t gsB, int64_t gsC, int64_t gsT,
+                             const float* z, int64_t B, int64_t C, int64_t T,
+                             int64_t sB, int64_t sC, int64_t sT,
+                             const float* E, const int32_t* idx, int64_t K,
+                             const float* g_loss, float coef, float* gz, vqb200_stream_t stream);
+
+/* ---- K3b': standard-VQ codebook gradient from mode-1 stats --------------- (row a11) --------
+ * gE[k,:] = g_loss[0]*coef*dw1[k,:],  coef = 2/(N*D),  dw1 from vqb200_ema_accumulate(mode=1). */
+int vqb200_vq_backward_codebook(const float* stats, int64_t K, int64_t D, const float* g_loss,
+                                float coef, float* gE, vqb200_stream_t stream);
+
+/* ---- K5: FSQ elementwise stage -------------------- models/vqvae.py:127-147,152-154 (a13) --
+ * z_e: contiguous [B,d,T] (post project_in).  z_hard = z + (rint(z) - z) (half-to-even, unbounded);
+ * idx[b,t] = (int64) trunc(sum_i fl(z_hard_i * basis_i)) evaluated left to right in fp32.
+ * Unique-code count without host sync: workspace (vqb200_unique_workspace_bytes(), zeroed by this
+ * call) holds a bitmap window plus a hash set for out-of-window codes.
+ * out2 = {perplexity = float(#unique), dcr = float(1 - #unique/codebook_size)} (device). */
+size_t vqb200_unique_workspace_bytes(void);
+int vqb200_fsq_forward(const float* z_e, int64_t B, int64_t d, int64_t T, const int32_t* basis,
+                       int64_t codebook_size, float* z_hard, int64_t* idx,
+                       void* workspace, float* out2, vqb200_stream_t stream);
+
+/* ---- K5: LFQ elementwise stage ----------------------- models/vqvae.py:171-191 (row a14) ----
+ * z_q = z_e + (sign - z_e) with sign = (z_e > 0 ? +1 : -1); idx[b,t] = sum_i (z_q_i > 0) << i;
+ * out3 = {loss = -mean(H_b(sigmoid(z_e)))*w, perplexity = #unique, dcr = 1 - #unique/2^d}. */
+int vqb200_lfq_forward(const float* z_e, int64_t B, int64_t d, int64_t T, float entropy_loss_weight,
+                       float* z_q, int64_t* idx, void* workspace, float* out3,
+                       vqb200_stream_t stream);
+/* dL/dz_e = g_zq + g_loss[0] * (-w/M) * dH/dp * p(1-p)   (closed form of autograd, row a14) */
+int vqb200_lfq_backward(const float* z_e, const float* g_zq, const float* g_loss, int64_t numel,
+                        float entropy_loss_weight, float* g_ze, vqb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* VQB200_H_ */

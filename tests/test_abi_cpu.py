@@ -1,0 +1,101 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds/loads and exports every symbol
+`include/vqb200.h` declares; the Python mirror keeps the reference's constructors, state_dict keys and
+error behaviour.  No compute calls (there is no GPU here)."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "vqb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vqb200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import vqb200
+    lib = vqb200._lib.load()
+    declared = _header_symbols()
+    assert declared, "header parse found nothing"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/vqb200.h but not exported"
+    assert sorted(vqb200._lib.exported_symbols()) == declared, "ctypes table and header disagree"
+    assert lib.vqb200_abi_version() == 1
+    assert isinstance(vqb200._lib.last_error(), str)
+    raw = ctypes.CDLL(vqb200._lib.library_path())
+    assert raw.vqb200_abi_version() == 1
+
+
+def test_size_queries_need_no_gpu():
+    import vqb200
+    lib = vqb200._lib.load()
+    # 1024 x 64 bf16 = 4 tiles of 32 KiB + 1024 fp32 norms
+    assert lib.vqb200_codebook_image_bytes(1024, 64) == 4 * 32768 + 1024 * 4
+    assert lib.vqb200_codebook_image_bytes(1000, 24) == 4 * 32768 + 1024 * 4
+    assert lib.vqb200_unique_workspace_bytes() > 256 * 1024
+    assert lib.vqb200_assign_workspace_bytes(1000) >= 1000 * 4
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    import vqb200
+    lib = vqb200._lib.load()
+    rc = lib.vqb200_vq_metrics(None, 4, 4, None, 4, 0.25, 1, None, None)
+    assert rc == -1 and "null" in vqb200._lib.last_error()
+    rc = lib.vqb200_fsq_forward(None, 1, 99, 1, None, 1000, None, None, None, None, None)
+    assert rc < 0
+
+
+def test_state_dict_keys_match_reference():
+    from models.vqvae import DualMotionVQVAE
+    table = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_keys.json")))
+    for key, ref in table.items():
+        arch, method = key.split("/")
+        if arch == "transformer" and method not in ("hybrid", "ema"):
+            continue                                  # same encoder keys; keep the CPU suite quick
+        m = DualMotionVQVAE(human_input_dim=126, robot_input_dim=29, hidden_dim=64, arch=arch, method=method,
+                            window_size=10)
+        mine = [[k, list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in m.state_dict().items()]
+        assert mine == ref, key
+
+
+def test_same_seed_same_initial_state_as_reference_order():
+    """Constructors consume the RNG in the reference's order (models/vqvae.py:19-26)."""
+    import vqb200
+    torch.manual_seed(3)
+    q = vqb200.VectorQuantizer(32, 8, use_ema=True)
+    torch.manual_seed(3)
+    emb = torch.nn.Embedding(32, 8)
+    emb.weight.data.uniform_(-1 / 32, 1 / 32)
+    ema_w = torch.empty(32, 8).normal_()
+    assert torch.equal(q.embedding.weight, emb.weight) and torch.equal(q.ema_w, ema_w)
+    assert q.decay == 0.99 and not hasattr(vqb200.VectorQuantizer(4, 4), "decay")
+
+
+def test_unknown_method_and_cpu_input_fail_loudly():
+    import vqb200
+    from models.vqvae import DualMotionVQVAE
+    with pytest.raises(ValueError):
+        DualMotionVQVAE(method="nope", arch="resnet_no_down")
+    for mod in (vqb200.VectorQuantizer(8, 4), vqb200.ResidualVQ(2, 8, 4), vqb200.FSQ([8, 5, 5, 5], 4, 4),
+                vqb200.LFQ(4), vqb200.HybridVQ(4, vq_codebook_size=8)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            mod(torch.randn(2, 4, 3))
+    loss, z, met = vqb200.IdentityVQ()(torch.randn(2, 4, 3))
+    assert float(loss) == 0.0 and float(met["perplexity"]) == 1.0
+
+
+def test_product_path_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under the package or models/ may import it."""
+    pkg = os.path.join(ROOT, "bridging-the-gap-of-robot-learning-via-distribution-reinforcement-learning-vq-vae_b200")
+    for base in (pkg, os.path.join(ROOT, "models")):
+        for dirpath, _, files in os.walk(base):
+            for f in files:
+                if f.endswith(".py"):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)

@@ -1,0 +1,88 @@
+"""world_size-2 gloo test of the data-parallel host logic (no GPU): sharding, the packed EMA-stats
+all-reduce and gradient averaging.  The per-rank statistics are produced by the oracle (tests may use
+it); the point is that reduce-then-finalize over shards equals the single-process full-batch update
+(SURVEY.md §8e), which is the semantics the CUDA path implements with NCCL."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, tmp):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import vqb200
+    from oracle import VQState, vq_forward
+    vqb200.dist.enable()
+    assert vqb200.dist.world_size() == world and vqb200.dist.rank() == rank
+
+    rng = np.random.default_rng(0)
+    K, D, B, T = 32, 8, 10, 3
+    E = rng.standard_normal((K, D)).astype(np.float32)
+    w = rng.standard_normal((K, D)).astype(np.float32)
+    z = rng.standard_normal((B, D, T)).astype(np.float32)
+    full = VQState(E.copy(), np.zeros(K, np.float32), w.copy(), 0.25, True, 0.99)
+    vq_forward(z, full, True)                                   # single-process full-batch oracle
+
+    lo, hi = vqb200.dist.shard_bounds(B)
+    covered = torch.zeros(B)
+    covered[lo:hi] = 1
+    dist.all_reduce(covered)
+    assert torch.equal(covered, torch.ones(B))                  # shards tile the batch exactly once
+
+    def reduce(cnt, dw):                                        # what RVQ stage s does between K3a and K3b
+        stats = torch.from_numpy(np.concatenate([dw.reshape(-1), cnt]))
+        vqb200.dist.all_reduce_stats(stats)
+        s = stats.numpy()
+        return s[K * D:].copy(), s[:K * D].reshape(K, D).copy()
+
+    mine = VQState(E.copy(), np.zeros(K, np.float32), w.copy(), 0.25, True, 0.99)
+    vq_forward(z[lo:hi], mine, True, stats_reduce=reduce)
+    np.testing.assert_allclose(mine.embedding, full.embedding, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(mine.ema_cluster_size, full.ema_cluster_size, rtol=1e-6)
+
+    # codebooks are bit-identical across ranks without a broadcast
+    e = torch.from_numpy(mine.embedding.copy())
+    gathered = [torch.empty_like(e) for _ in range(world)]
+    dist.all_gather(gathered, e)
+    assert all(torch.equal(g, gathered[0]) for g in gathered)
+
+    # DDP-style gradient averaging
+    p = torch.nn.Parameter(torch.zeros(5))
+    p.grad = torch.full((5,), float(rank + 1))
+    q = torch.nn.Parameter(torch.zeros(3))                      # no grad: skipped
+    calls = vqb200.dist.average_gradients([p, q])
+    assert calls == 1 and torch.allclose(p.grad, torch.full((5,), (1 + world) / 2))
+    open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_two_rank_stats_allreduce(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_shard_bounds_cover():
+    import vqb200
+    for n in (0, 1, 7, 8, 1000):
+        for w in (1, 2, 3, 8):
+            b = [vqb200.dist.shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
