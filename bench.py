@@ -1,0 +1,468 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the quantizer hot path (quantized vectors / second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+Headline workload (BASELINE.json configs[2], the config the "1/2/4/8 B200" metric is quoted on):
+  ResidualVQ, S=4 stages, K=1024 codes, D=64, training mode (forward + EMA update + backward) on
+  synthetic latents z ~ 0.5*N(0,1) of shape [1 000 000, 64, 10] PER GPU (N = 10 M vectors / GPU, weak
+  scaling: batch sharded on dim 0, the per-stage EMA statistics all-reduced with NCCL over NVLink).
+One "step" = one full pass (fwd + EMA + bwd) over the batch.  One JSON line is printed by rank 0.
+
+`value`     : whole-job vectors/s with inputs resident in HBM (CUDA events, max over ranks).
+`e2e`       : same metric through the public nn.Module call with the step's input copied from pinned HOST
+              memory and the result (loss, perplexity, int32 indices) read back to the host every step.
+`roofline`  : dominant kernel (K1 fused distance+argmin) timed alone with CUDA events; algorithmic flops
+              2*N*K*D per launch against the measured bf16 tensor peak (MEASURED_PEAKS.json).
+`cpu_baseline`: the numpy oracle port of the reference algorithm on this box's host cores, on a bounded
+              sample of the same workload.  `--impl reference` prints that arm as its own line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "quantized vectors/sec (VQ fwd+EMA+bwd)"
+UNIT = "vectors/s"
+
+WORKLOADS = {
+    # name: (kind, S, K, D, windows B, T)
+    "cfg3_rvq4_k1024_d64": dict(kind="rvq", S=4, K=1024, D=64, B=1_000_000, T=10),
+    "cfg1_ema_k1024_d64": dict(kind="vq", S=1, K=1024, D=64, B=4096, T=10),
+    "cfg5_ema_k4096_d128": dict(kind="vq", S=1, K=4096, D=128, B=4_194_304, T=1),
+}
+HEADLINE = "cfg3_rvq4_k1024_d64"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                        bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                        source="measured (MEASURED_PEAKS.json)")
+        except Exception:
+            pass
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0,
+                source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: numpy oracle port of the reference algorithm
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_arm(cfg, steps, warmup, sample_windows=None):
+    """Times forward + EMA update + backward of the reference algorithm (oracle port, numpy/OpenBLAS on all
+    host cores) on a bounded sample of the workload.  The reference materialises N x K fp32 matrices, so the
+    sample is a chunk that fits."""
+    import numpy as np
+    from oracle import VQState, rvq_forward, rvq_backward
+    K, D, S, T = cfg["K"], cfg["D"], cfg["S"], cfg["T"]
+    Bs = sample_windows or max(1, min(cfg["B"], 16384 // T))
+    rng = np.random.default_rng(1237)
+    stages = []
+    for s in range(S):
+        E = (0.25 * rng.standard_normal((K, D))).astype(np.float32)
+        stages.append(VQState(E.copy(), np.ones(K, np.float32), E.copy(), 0.25, True, 0.99))
+    z = (0.5 * rng.standard_normal((Bs, D, T))).astype(np.float32)
+    g = rng.standard_normal((Bs, D, T)).astype(np.float32)
+
+    def step():
+        fw = rvq_forward(z, stages, True)
+        rvq_backward(fw, stages, g, 1.0)
+
+    for _ in range(max(1, min(warmup, 2))):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    n = Bs * T
+    return dict(value=n / med, unit=UNIT, cores=os.cpu_count(), kind="port",
+                sample=f"{Bs} windows x T={T} = {n} vectors per step (chunk of the workload; the reference "
+                       f"materialises N x K), median of {steps} steps, numpy/OpenBLAS fp32",
+                ms_per_step=med * 1e3)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def build_module(vqb200, torch, cfg, dev, seed=42):
+    K, D, S = cfg["K"], cfg["D"], cfg["S"]
+    torch.manual_seed(seed)
+    if cfg["kind"] == "rvq":
+        mod = vqb200.ResidualVQ(S, K, D, use_ema=True)
+        layers = list(mod.layers)
+    else:
+        mod = vqb200.VectorQuantizer(K, D, use_ema=True)
+        layers = [mod]
+    with torch.no_grad():
+        for l in layers:                      # non-degenerate start, identical on every rank
+            l.embedding.weight.normal_(0, 0.25)
+            l.ema_w.copy_(l.embedding.weight)
+            l.ema_cluster_size.fill_(1.0)
+    return mod.to(dev).train(), layers
+
+
+def run_gpu(args):
+    import torch
+    import vqb200
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        vqb200.dist.enable()
+    cfg = dict(WORKLOADS[args.workload])
+    if args.windows:
+        cfg["B"] = args.windows
+    K, D, S, B, T = cfg["K"], cfg["D"], cfg["S"], cfg["B"], cfg["T"]
+    N = B * T
+    peaks = load_peaks()
+    mod, layers = build_module(vqb200, torch, cfg, dev)
+    gen = torch.Generator(device=dev).manual_seed(1237 + rank)
+    z = torch.randn((B, D, T), generator=gen, device=dev).mul_(0.5)
+    g = torch.randn((B, D, T), generator=gen, device=dev)
+    one = torch.ones((), device=dev)
+
+    def step(zin):
+        zin.grad = None
+        loss, q, met = mod(zin)
+        torch.autograd.backward([q, loss], [g, one])
+        return loss, met
+
+    zr = z.requires_grad_(True)
+    for _ in range(args.warmup):
+        step(zr)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = vqb200._lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, met = step(zr)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = vqb200._lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = N * world / (ms_per_step * 1e-3)
+
+    # ---- end-to-end: pinned host input -> H2D -> fwd+EMA+bwd -> D2H of loss / perplexity / indices ----
+    e2e = None
+    try:
+        z_host = torch.empty((B, D, T), dtype=torch.float32, pin_memory=True)
+        z_host.copy_(z.detach())
+        idx_host = torch.empty((S, B, T), dtype=torch.int32, pin_memory=True)
+        sc_host = torch.empty(2, dtype=torch.float32, pin_memory=True)
+        z_dev = torch.empty_like(z.detach()).requires_grad_(True)
+
+        def e2e_step():
+            with torch.no_grad():
+                z_dev.copy_(z_host, non_blocking=True)
+            loss, met = step(z_dev)
+            idx = mod.last_indices if cfg["kind"] == "rvq" else mod.last_indices.unsqueeze(0)
+            idx_host.copy_(idx, non_blocking=True)
+            sc_host.copy_(torch.stack([loss.detach(), met["perplexity"]]), non_blocking=True)
+
+        n_e2e = max(3, min(args.steps, 5))
+        e2e_step(); e2e_step()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        a1.record()
+        barrier()
+        ems = a0.elapsed_time(a1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ems], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        e2e = {"value": N * world / (ems / n_e2e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(z_host.numel() * 4), "d2h_bytes_per_step": int(idx_host.numel() * 4 + 8),
+               "ms_per_step": ems / n_e2e, "steps": n_e2e}
+        del z_host, idx_host, z_dev
+    except Exception as ex:  # pragma: no cover
+        e2e = {"error": repr(ex)}
+
+    # ---- roofline of the dominant kernel (K1), timed alone ----
+    roof = None
+    if rank == 0:
+        st = layers[0]._state(dev)
+        w0 = layers[0].embedding.weight
+        zz = z.detach()
+        for _ in range(3):
+            vqb200.vq_assign(zz, w0, st)
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        k0.record()
+        for _ in range(reps):
+            vqb200.vq_assign(zz, w0, st)
+        k1.record()
+        torch.cuda.synchronize()
+        kms = k0.elapsed_time(k1) / reps
+        flops = 2.0 * N * K * D
+        bytes_alg = N * (4 * D + 4)
+        t_tensor = flops / (peaks["bf16_tflops"] * 1e12)
+        t_hbm = bytes_alg / (peaks["hbm_gbs"] * 1e9)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload)
+            except Exception:
+                traffic = None
+        if t_tensor >= t_hbm:
+            roof = {"kernel": "vq_assign (K1 fused distance+argmin)", "bound": "tensor",
+                    "achieved": flops / (kms * 1e-3) / 1e12, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": (flops / (kms * 1e-3) / 1e12) / peaks["bf16_tflops"], "traffic": traffic,
+                    "ms_per_launch": kms, "peak_source": peaks["source"] + ", burst bf16"}
+        else:
+            roof = {"kernel": "vq_assign (K1 fused distance+argmin)", "bound": "hbm",
+                    "achieved": bytes_alg / (kms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": (bytes_alg / (kms * 1e-3) / 1e9) / peaks["hbm_gbs"], "traffic": traffic,
+                    "ms_per_launch": kms, "peak_source": peaks["source"]}
+        # whole-step floor for context: max(bytes/BW, flops/P)
+        step_flops = 2.0 * N * S * K * D
+        step_bytes = N * (20 * D + 4 * S + 4)
+        floor = max(step_flops / (peaks["bf16_tflops_sustained"] * 1e12), step_bytes / (peaks["hbm_gbs"] * 1e9))
+        roof["step_floor_ms"] = floor * 1e3
+        roof["step_frac_of_floor"] = floor * 1e3 / ms_per_step
+
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    extras = None
+    if world == 1 and not args.no_cpu:
+        cpu = cpu_reference_arm(cfg, steps=3, warmup=1)
+    if world == 1 and not args.no_extras:
+        extras = run_extras(torch, vqb200, dev, peaks)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: ResidualVQ S={S} K={K} D={D} EMA training step (fwd+EMA+bwd), "
+                               f"z [{B},{D},{T}] fp32 per GPU = {N} vectors/GPU, batch sharded on dim 0, per-stage "
+                               f"EMA stats all-reduced (NCCL)" if cfg["kind"] == "rvq" else
+                               f"{args.workload}: VectorQuantizer K={K} D={D} EMA training step, z [{B},{D},{T}] per GPU",
+                   "vectors_per_gpu": N, "parallelism": f"dp{world}",
+                   "l2": "inputs larger than L2 (2.56 GB per tensor per GPU)" if N * D * 4 > 256e6 else "L2 not flushed (small input)"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roof, "cpu_baseline": cpu,
+        "loss": float(loss.item()), "perplexity": float(met["perplexity"].item()),
+    }
+    if extras:
+        out["other_workloads"] = extras
+    print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def run_extras(torch, vqb200, dev, peaks):
+    """Short measurements of the other BASELINE.json configs (parity-test cases, not the headline)."""
+    res = {}
+
+    def timeit(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    try:
+        # cfg1: EMA-VQ K=1024, z [4096,64,10]
+        cfg = WORKLOADS["cfg1_ema_k1024_d64"]
+        mod, _ = build_module(vqb200, torch, cfg, dev)
+        z = torch.randn(cfg["B"], cfg["D"], cfg["T"], device=dev).requires_grad_(True)
+        g = torch.randn_like(z); one = torch.ones((), device=dev)
+
+        def s1():
+            z.grad = None
+            loss, q, _ = mod(z)
+            torch.autograd.backward([q, loss], [g, one])
+        l0 = vqb200._lib.launch_count()
+        ms = timeit(s1, 20)
+        res["cfg1_ema_k1024_n40960"] = {"us_per_step": ms * 1e3, "vectors_per_s": cfg["B"] * cfg["T"] / (ms * 1e-3),
+                                        "launches_per_step": (vqb200._lib.launch_count() - l0) / 23}
+        # cfg2: Hybrid on the permuted [512,64,1] view
+        torch.manual_seed(42)
+        hy = vqb200.HybridVQ(64, [8, 5, 5, 5], vq_codebook_size=512).to(dev).train()
+        zz = torch.randn(512, 1, 64, device=dev).permute(0, 2, 1).requires_grad_(True)
+        g2 = torch.randn(512, 64, 1, device=dev)
+
+        def s2():
+            zz.grad = None
+            loss, q, _ = hy(zz)
+            torch.autograd.backward([q, loss], [g2, one])
+        l0 = vqb200._lib.launch_count()
+        ms = timeit(s2, 30)
+        res["cfg2_hybrid_n512"] = {"us_per_step": ms * 1e3, "vectors_per_s": 512 / (ms * 1e-3),
+                                   "vqb200_launches_per_step": (vqb200._lib.launch_count() - l0) / 33}
+        # cfg4: FSQ / LFQ elementwise stage, 1 048 576 windows x 10
+        B = 1_048_576
+        ze = 2.0 * torch.randn(B, 4, 10, device=dev)
+        basis = torch.tensor([1, 8, 40, 200], dtype=torch.int32, device=dev)
+        ms = timeit(lambda: vqb200.fsq_round(ze, basis, 1000), 10)
+        n = B * 10
+        res["cfg4_fsq_elementwise_n10m"] = {"vectors_per_s": n / (ms * 1e-3), "GBps_algorithmic": n * 40 / (ms * 1e-3) / 1e9,
+                                            "frac_of_hbm": n * 40 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        zl = torch.randn(B, 10, 10, device=dev)
+        ms = timeit(lambda: vqb200.lfq_sign(zl, 0.1), 10)
+        res["cfg4_lfq_elementwise_n10m"] = {"vectors_per_s": n / (ms * 1e-3), "GBps_algorithmic": n * 88 / (ms * 1e-3) / 1e9,
+                                            "frac_of_hbm": n * 88 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        del ze, zl
+        # cfg5 point: EMA-VQ K=4096, D=128, N = 4 M (assignment only + full step)
+        cfg = WORKLOADS["cfg5_ema_k4096_d128"]
+        mod5, layers5 = build_module(vqb200, torch, cfg, dev)
+        z5 = torch.randn(cfg["B"], cfg["D"], 1, device=dev)
+        st5 = layers5[0]._state(dev)
+        ms = timeit(lambda: vqb200.vq_assign(z5, layers5[0].embedding.weight, st5), 2, warm=1)
+        fl = 2.0 * cfg["B"] * cfg["K"] * cfg["D"]
+        res["cfg5_assign_k4096_d128_n4m"] = {"ms": ms, "vectors_per_s": cfg["B"] / (ms * 1e-3), "TFLOPs": fl / (ms * 1e-3) / 1e12,
+                                             "frac_of_bf16_peak": fl / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"]}
+    except Exception as ex:  # pragma: no cover
+        res["error"] = repr(ex)
+    return res
+
+
+def run_reference(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = dict(WORKLOADS[args.workload])
+    K, D, S, B, T = cfg["K"], cfg["D"], cfg["S"], cfg["B"], cfg["T"]
+    r = cpu_reference_arm(cfg, steps=max(1, args.steps), warmup=args.warmup)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: ResidualVQ S={S} K={K} D={D} EMA training step (fwd+EMA+bwd), "
+                               f"reference algorithm on host CPU cores, bounded sample", "parallelism": "cpu"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="vqb200", choices=["vqb200", "reference"])
+    ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
+    ap.add_argument("--windows", type=int, default=0, help="override the number of windows B (development only)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "vqb200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

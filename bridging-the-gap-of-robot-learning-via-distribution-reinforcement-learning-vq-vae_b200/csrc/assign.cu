@@ -25,7 +25,7 @@ int vqb200_vq_assign(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB
                      int32_t* idx, float* best, void* workspace, size_t workspace_bytes, int algo,
                      vqb200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  VQ_CHECK_ARG(z && E && ee && idx, VQB200_EINVAL, "vq_assign: null pointer");
+  VQ_CHECK_ARG((z && E && ee && idx) || B * T == 0, VQB200_EINVAL, "vq_assign: null pointer");
   VQ_CHECK_ARG(B >= 0 && C > 0 && T > 0 && K > 0 && K < (1LL << 30) && C < (1 << 16), VQB200_ESHAPE,
                "vq_assign: bad shape B=%lld C=%lld T=%lld K=%lld", (long long)B, (long long)C, (long long)T, (long long)K);
   VQ_CHECK_ARG(B * T < (1LL << 31), VQB200_ESHAPE, "vq_assign: N=%lld exceeds int32 row ids", (long long)(B * T));

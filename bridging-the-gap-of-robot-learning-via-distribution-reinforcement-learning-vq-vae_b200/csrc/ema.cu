@@ -228,7 +228,7 @@ int vqb200_ema_accumulate(const float* z, int64_t B, int64_t C, int64_t T, int64
                           const int32_t* idx, const float* E, int64_t K, float* stats, int mode,
                           vqb200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  VQ_CHECK_ARG(z && idx && stats, VQB200_EINVAL, "ema_accumulate: null pointer");
+  VQ_CHECK_ARG(stats && ((z && idx) || B * T == 0), VQB200_EINVAL, "ema_accumulate: null pointer");
   VQ_CHECK_ARG(mode == 0 || (mode == 1 && E), VQB200_EINVAL, "ema_accumulate: mode %d needs E", mode);
   VQ_CHECK_ARG(B >= 0 && C > 0 && T > 0 && K > 0, VQB200_ESHAPE, "ema_accumulate: bad shape");
   const int D = (int)C;
@@ -274,7 +274,7 @@ int vqb200_ema_finalize(const float* stats, float* ema_cluster_size, float* ema_
 
 int vqb200_vq_histogram(const int32_t* idx, int64_t N, int64_t K, float* cnt, vqb200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  VQ_CHECK_ARG(idx && cnt, VQB200_EINVAL, "vq_histogram: null pointer");
+  VQ_CHECK_ARG(cnt && (idx || N == 0), VQB200_EINVAL, "vq_histogram: null pointer");
   VQ_CHECK_ARG(N >= 0 && K > 0, VQB200_ESHAPE, "vq_histogram: bad shape");
   VQ_CUDA(cudaMemsetAsync(cnt, 0, (size_t)K * sizeof(float), stream));
   if (N == 0) return VQB200_OK;

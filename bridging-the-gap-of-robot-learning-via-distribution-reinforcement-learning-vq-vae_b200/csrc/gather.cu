@@ -111,7 +111,7 @@ int vqb200_vq_gather_st(const float* z, int64_t B, int64_t C, int64_t T, int64_t
                         const float* E, const int32_t* idx, int64_t K, float* out, float* residual,
                         float* accum, int accum_init, double* sse, vqb200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  VQ_CHECK_ARG(z && E && idx && sse, VQB200_EINVAL, "vq_gather_st: null pointer");
+  VQ_CHECK_ARG(sse && ((z && E && idx) || B * C * T == 0), VQB200_EINVAL, "vq_gather_st: null pointer");
   VQ_CHECK_ARG(B >= 0 && C > 0 && T > 0 && K > 0 && C * T < (1LL << 31), VQB200_ESHAPE, "vq_gather_st: bad shape");
   VQ_CUDA(cudaMemsetAsync(sse, 0, sizeof(double), stream));
   const long long total = B * C * T;
@@ -138,7 +138,7 @@ int vqb200_vq_backward_input(const float* g, int64_t gsB, int64_t gsC, int64_t g
                              const float* E, const int32_t* idx, int64_t K, const float* g_loss, float coef,
                              float* gz, vqb200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  VQ_CHECK_ARG(z && E && idx && gz, VQB200_EINVAL, "vq_backward_input: null pointer");
+  VQ_CHECK_ARG((z && E && idx && gz) || B * C * T == 0, VQB200_EINVAL, "vq_backward_input: null pointer");
   VQ_CHECK_ARG(B >= 0 && C > 0 && T > 0 && K > 0 && C * T < (1LL << 31), VQB200_ESHAPE, "vq_backward_input: bad shape");
   const long long total = B * C * T;
   if (total == 0) return VQB200_OK;

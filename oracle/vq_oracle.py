@@ -245,9 +245,11 @@ def fsq_quantize(z_e: np.ndarray, levels: Sequence[int]) -> Dict[str, object]:
     }
 
 
-def fsq_forward(z: np.ndarray, levels: Sequence[int], w_in, b_in, w_out, b_out) -> Dict[str, object]:
-    """`FSQ.forward` incl. both 1x1 projections                 models/vqvae.py:125-150."""
-    z_e = conv1x1(z, w_in, b_in)                              # :126
+def fsq_forward(z: np.ndarray, levels: Sequence[int], w_in, b_in, w_out, b_out, z_e=None) -> Dict[str, object]:
+    """`FSQ.forward` incl. both 1x1 projections                 models/vqvae.py:125-150.
+    z_e: optional override of the post-`project_in` tensor (bit-exactness of the rounding is only
+    defined from that tensor onward, SURVEY.md §7 "FSQ/LFQ bit-exactness")."""
+    z_e = conv1x1(z, w_in, b_in) if z_e is None else np.asarray(z_e, F)   # :126
     r = fsq_quantize(z_e, levels)
     r["z_e"] = z_e
     r["quantized"] = conv1x1(r["z_hard"], w_out, b_out)       # :133-134
@@ -309,10 +311,10 @@ def lfq_forward(z: np.ndarray, w_in, b_in, w_out, b_out, entropy_loss_weight: fl
 def hybrid_forward(z: np.ndarray, levels: Sequence[int], w_in, b_in, w_out, b_out,
                    stages: Sequence[VQState], training: bool = True,
                    force_indices: Optional[Sequence[np.ndarray]] = None,
-                   stats_reduce: Optional[Callable] = None) -> Dict[str, object]:
+                   stats_reduce: Optional[Callable] = None, z_e=None) -> Dict[str, object]:
     """`HybridVQ.forward`: FSQ base + RVQ on the residual       models/vqvae.py:219-241."""
     z = np.asarray(z, F)
-    f = fsq_forward(z, levels, w_in, b_in, w_out, b_out)      # :221
+    f = fsq_forward(z, levels, w_in, b_in, w_out, b_out, z_e)  # :221
     residual = z - f["quantized"]                             # :224
     r = rvq_forward(residual, stages, training, force_indices, stats_reduce)   # :228
     return {
