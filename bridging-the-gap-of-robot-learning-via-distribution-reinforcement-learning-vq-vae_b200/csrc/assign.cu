@@ -35,10 +35,11 @@ int vqb200_vq_assign(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB
   bool use_tc = false;
   if (algo == VQB200_ASSIGN_TC) {
     VQ_CHECK_ARG(image && info && workspace, VQB200_EINVAL, "vq_assign(TC): image, info and workspace are required");
+    VQ_CHECK_ARG(!best, VQB200_EUNSUPPORTED, "vq_assign(TC): the winning distance is only produced by the SIMT algorithm");
     VQ_CHECK_ARG(assign_tc_eligible(zv, (int)K, D), VQB200_EUNSUPPORTED, "vq_assign(TC): shape K=%lld D=%d not eligible", (long long)K, D);
     use_tc = true;
   } else if (algo == VQB200_ASSIGN_AUTO) {
-    use_tc = image && info && workspace && assign_tc_eligible(zv, (int)K, D) &&
+    use_tc = image && info && workspace && !best && assign_tc_eligible(zv, (int)K, D) &&
              workspace_bytes >= assign_tc_workspace_bytes(zv.N) && zv.N >= 2048;
   } else {
     VQ_CHECK_ARG(algo == VQB200_ASSIGN_SIMT, VQB200_EINVAL, "vq_assign: unknown algo %d", algo);

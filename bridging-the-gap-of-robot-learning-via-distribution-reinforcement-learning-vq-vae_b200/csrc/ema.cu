@@ -24,13 +24,13 @@ codebook_prepare_kernel(const float* __restrict__ E, int K, int D, float* __rest
       float v = (k < K && c < D) ? __ldg(E + (size_t)k * D + c) : 0.f;
       s = fmaf(v, v, s);
       bad |= !(fabsf(v) <= 3.0e38f);
-      if (image) *reinterpret_cast<__nv_bfloat16*>(image + img_elem_offset(k, c, Dp)) = __float2bfloat16_rn(v);
+      if (image) img_store(image, k, c, Dp, v);
     }
     s = warp_sum(s);
     bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {
       if (k < K) { ee[k] = s; info_update(info, s, bad); }
-      if (ee_img) ee_img[k] = (k < K) ? s : INFINITY;
+      if (ee_img) ee_img[k] = (k < K) ? -0.5f * s : -INFINITY;
     }
   }
 }
@@ -181,13 +181,13 @@ ema_finalize_w_kernel(const float* __restrict__ dw, float* __restrict__ w, float
         bad |= !(fabsf(e) <= 3.0e38f);
       }
       s = fmaf(e, e, s);
-      if (image) *reinterpret_cast<__nv_bfloat16*>(image + img_elem_offset(k, c, Dp)) = __float2bfloat16_rn(e);
+      if (image) img_store(image, k, c, Dp, e);
     }
     s = warp_sum(s);
     bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {
       if (k < K) { if (ee) ee[k] = s; info_update(info, s, bad); }
-      if (ee_img) ee_img[k] = (k < K) ? s : INFINITY;
+      if (ee_img) ee_img[k] = (k < K) ? -0.5f * s : -INFINITY;
     }
   }
 }

@@ -1,0 +1,75 @@
+"""Development check of the tcgen05 assignment path: TC (algo=2) vs exact SIMT (algo=1)."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import vqb200
+from vqb200 import _lib
+
+dev = torch.device("cuda:0")
+
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def case(B, T, K, regime="small", seed=0, time_it=False, perm=False):
+    D = 64
+    torch.manual_seed(seed)
+    W = torch.randn(K, D, device=dev)
+    if regime == "small":
+        W *= 0.3
+    elif regime == "init":
+        W = (torch.rand(K, D, device=dev) * 2 - 1) / K
+    elif regime == "degenerate":
+        W[: K // 2] *= 1e5
+    elif regime == "dup":
+        W[K // 2:] = W[: K - K // 2]
+    st = vqb200.QuantizerState(K, D, dev)
+    if perm:
+        z = (0.5 * torch.randn(B, T, D, device=dev)).permute(0, 2, 1)
+    else:
+        z = 0.5 * torch.randn(B, D, T, device=dev)
+    i_simt = vqb200.vq_assign(z, W, st, _lib.ASSIGN_SIMT)
+    i_tc = vqb200.vq_assign(z, W, st, _lib.ASSIGN_TC)
+    torch.cuda.synchronize()
+    ws = st._assign_ws.view(torch.int32)
+    flagged, err = int(ws[0]), int(ws[1])
+    mism = int((i_simt != i_tc).sum())
+    out = dict(B=B, T=T, K=K, regime=regime, perm=perm, N=B * T, mismatches=mism, flagged=flagged, err=err)
+    if mism:
+        bad = (i_simt != i_tc).reshape(-1).nonzero().reshape(-1)[:5]
+        out["first_bad_rows"] = bad.tolist()
+        out["simt"] = i_simt.reshape(-1)[bad].tolist()
+        out["tc"] = i_tc.reshape(-1)[bad].tolist()
+    if time_it:
+        out["ms_tc"] = timeit(lambda: vqb200.vq_assign(z, W, st, _lib.ASSIGN_TC))
+        out["ms_simt"] = timeit(lambda: vqb200.vq_assign(z, W, st, _lib.ASSIGN_SIMT), reps=2, warm=1)
+        fl = 2.0 * B * T * K * D
+        out["tc_TFLOPs"] = fl / (out["ms_tc"] * 1e-3) / 1e12
+    print(json.dumps(out), flush=True)
+    return mism
+
+
+if __name__ == "__main__":
+    total = 0
+    total += case(2, 128, 128)                 # one CTA tile, one code tile
+    total += case(1, 256, 256, perm=True)
+    total += case(100, 10, 1024)
+    total += case(4096, 10, 1024, time_it=True)
+    total += case(4096, 10, 1000, "normal")
+    total += case(512, 1, 512, "init", perm=True)
+    total += case(3686, 10, 1024, "degenerate")
+    total += case(3000, 7, 300, "dup")
+    total += case(100000, 10, 1024, time_it=True)
+    total += case(1000000, 10, 1024, time_it=True)
+    total += case(1000000, 1, 4096, "normal", time_it=True, perm=True)
+    print("TOTAL MISMATCHES", total)
