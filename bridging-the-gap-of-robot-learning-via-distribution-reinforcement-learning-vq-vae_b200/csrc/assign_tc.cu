@@ -38,12 +38,15 @@ constexpr int TILE_M = 128;
 constexpr int BM = RT * TILE_M;             // 256 rows per CTA iteration
 constexpr int BN = IMG_TILE_CODES;          // 128 codes per accumulator
 constexpr int D = 64;
-constexpr int NST = 4;                      // codebook ring stages
+constexpr int NST = 2;                      // codebook ring stages
 constexpr int A_HALF = TILE_M * 128;        // 16384 B: one of {hi, lo} for one row tile
 constexpr int SMEM_A = RT * 2 * A_HALF;     // 65536
-constexpr int SMEM_B = NST * IMG_TILE_BYTES;    // 131072
+constexpr int STG_BYTES = 36864;            // raw fp32 z staging per row tile (bulk-TMA prefetched)
+constexpr int SMEM_STG = RT * STG_BYTES;    // 73728
+constexpr int SMEM_B = NST * IMG_TILE_BYTES;    // 65536
 constexpr int SMEM_BAR = 256;
-constexpr int SMEM_TOTAL = SMEM_A + SMEM_B + SMEM_BAR + 1024;   // + alignment slack
+constexpr int SMEM_TOTAL = SMEM_A + SMEM_STG + SMEM_B + SMEM_BAR + 1024;   // + alignment slack
+enum StageMode : int { STG_DIRECT = 0, STG_ROWS = 1, STG_BCT = 2 };
 constexpr int NTHREADS = 320;
 constexpr unsigned SPIN_LIMIT = 1u << 22;   // bounded waits: a protocol bug traps instead of hanging the GPU
 
@@ -127,6 +130,7 @@ struct Params {
   const float* neg_half_ee;       // ... followed by -|E_k|^2/2 (padded with -inf)
   const float* info;              // {max |E_k|, nonfinite flag}
   int K, NT;                      // codes, number of 128-code tiles
+  int stage_mode;                 // how raw z reaches shared memory (StageMode)
   long long ntiles;               // 256-row CTA tiles
   int32_t* idx;
   int32_t* list;                  // rows that need the exact kernel
@@ -134,28 +138,65 @@ struct Params {
   int* err;
 };
 
+// Byte range of the raw fp32 input that covers rows [n0, n0+rows) (staged modes only).
+struct StagePlan { const float* src; uint32_t bytes; long long b_lo; };
+__device__ __forceinline__ StagePlan stage_plan(const Params& p, long long n0, int rows) {
+  StagePlan sp;
+  if (p.stage_mode == STG_ROWS) {
+    sp.src = p.z.p + n0 * D; sp.bytes = (uint32_t)rows * (D * 4); sp.b_lo = 0;
+  } else {
+    const long long T = p.z.T;
+    sp.b_lo = n0 / T;
+    const long long b_hi = (n0 + rows - 1) / T;
+    sp.src = p.z.p + sp.b_lo * (D * T);
+    sp.bytes = (uint32_t)((b_hi - sp.b_lo + 1) * (D * T * 4));
+  }
+  return sp;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {      // a -> low half, b -> high half
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// (score & ~127) | column in ONE alu op: lop3 with LUT (a & c) | b
+__device__ __forceinline__ float pack_col(float s, uint32_t col, uint32_t mask) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEC;" : "=r"(r) : "r"(__float_as_uint(s)), "r"(col), "r"(mask));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 vq_assign_tc_kernel(const Params p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;                       // [RT][hi,lo][16384]
-  unsigned char* sB = smem + SMEM_A;              // [NST][32768]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_A + SMEM_B);
-  // barrier map
-  uint64_t* full = bars;                 // [NST]
-  uint64_t* empty = bars + NST;          // [NST]
-  uint64_t* tfull = bars + 2 * NST;      // [2 stages][RT]
-  uint64_t* tempty = tfull + 2 * RT;     // [2 stages][RT]
-  uint64_t* afull = tempty + 2 * RT;     // [RT]
-  uint64_t* aempty = afull + RT;         // [RT]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + RT);
+  unsigned char* sS = smem + SMEM_A;              // [RT][STG_BYTES]  raw fp32 staging
+  unsigned char* sB = sS + SMEM_STG;              // [NST][32768]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SMEM_B);
+  uint64_t* full = bars;                 // [NST]      codebook tile landed
+  uint64_t* empty = full + NST;          // [NST]      codebook tile consumed by the MMAs
+  uint64_t* tfull = empty + NST;         // [2][RT]    accumulator ready
+  uint64_t* tempty = tfull + 2 * RT;     // [2][RT]    accumulator drained
+  uint64_t* afull = tempty + 2 * RT;     // [RT]       A operands written
+  uint64_t* aempty = afull + RT;         // [RT]       A operands no longer read
+  uint64_t* sfull = aempty + RT;         // [RT]       raw z staged
+  uint64_t* sempty = sfull + RT;         // [RT]       staging consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + RT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
     for (int i = 0; i < 2 * RT; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4); }
-    for (int r = 0; r < RT; ++r) { mbar_init(smem_u32(afull + r), 4); mbar_init(smem_u32(aempty + r), 1); }
+    for (int r = 0; r < RT; ++r) {
+      mbar_init(smem_u32(afull + r), 4); mbar_init(smem_u32(aempty + r), 1);
+      mbar_init(smem_u32(sfull + r), 1); mbar_init(smem_u32(sempty + r), 4);
+    }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
@@ -166,10 +207,24 @@ vq_assign_tc_kernel(const Params p) {
   const int NT = p.NT;
 
   if (warp == 0) {
-    // ================= bulk-TMA producer =================
+    // ================= bulk-TMA producer: raw z slabs + codebook tiles =================
     if (lane == 0) {
-      unsigned it = 0;
+      unsigned it = 0, staged[RT] = {0, 0};
       for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        if (p.stage_mode != STG_DIRECT) {
+#pragma unroll
+          for (int rt = 0; rt < RT; ++rt) {
+            const long long n0 = tile * BM + (long long)rt * TILE_M;
+            const int rows = (int)max(0LL, min((long long)TILE_M, p.z.N - n0));
+            if (rows > 0) {
+              const StagePlan sp = stage_plan(p, n0, rows);
+              mbar_wait(smem_u32(sempty + rt), (staged[rt] & 1) ^ 1, p.err, 7);
+              mbar_expect_tx(smem_u32(sfull + rt), sp.bytes);
+              bulk_g2s(smem_u32(sS + (size_t)rt * STG_BYTES), sp.src, sp.bytes, smem_u32(sfull + rt));
+              ++staged[rt];
+            }
+          }
+        }
         for (int j = 0; j < NT; ++j, ++it) {
           const unsigned s = it % NST, ph = (it / NST) & 1;
           mbar_wait(smem_u32(empty + s), ph ^ 1, p.err, 1);
@@ -212,51 +267,74 @@ vq_assign_tc_kernel(const Params p) {
       }
     }
   } else {
-    // ================= loader + epilogue groups (4 warps = 128 rows each) =================
+    // ================= converter + epilogue groups (4 warps = 128 rows each) =================
     const int rt = (warp - 2) >> 2;
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int gtid = (warp - 2 - rt * 4) * 32 + lane;   // 0..127 inside the group (load cooperation)
     const int row = q * 32 + lane;                // accumulator lane == row inside the row tile
     unsigned char* a_hi = sA + (size_t)rt * 2 * A_HALF;
     unsigned char* a_lo = a_hi + A_HALF;
+    const float* stg = reinterpret_cast<const float*>(sS + (size_t)rt * STG_BYTES);
     const float emax = p.info[0];
     const bool cb_bad = p.info[1] != 0.f;
-    unsigned it = 0, tile_i = 0;
+    const uint32_t mask = 0xFFFFFF80u;
+    unsigned it = 0, tile_i = 0, staged = 0;
     for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_i) {
       const long long n0 = tile * BM + (long long)rt * TILE_M;
       const int rows = (int)max(0LL, min((long long)TILE_M, p.z.N - n0));
-      mbar_wait(smem_u32(aempty + rt), (tile_i & 1) ^ 1, p.err, 5);       // MMAs of the previous tile are done with A
-      if (rows < TILE_M) {
-        for (int i = gtid; i < 2 * A_HALF / 16; i += 128) reinterpret_cast<uint4*>(a_hi)[i] = make_uint4(0, 0, 0, 0);
-        group_sync(1 + rt);
+      const bool use_stage = (p.stage_mode != STG_DIRECT) && rows > 0;
+      // ---- this thread's row: fp32 -> (hi, lo) bf16, swizzled K-major A operand; exact |x|^2 ----
+      long long goff = 0; int sstride = 1; const float* src = nullptr;
+      if (row < rows) {
+        const long long n = n0 + row;
+        if (p.stage_mode == STG_ROWS) { src = stg + row * D; sstride = 1; }
+        else if (p.stage_mode == STG_BCT) {
+          const StagePlan sp = stage_plan(p, n0, rows);
+          const long long b = n / p.z.T; const int t = (int)(n - b * p.z.T);
+          src = stg + (b - sp.b_lo) * (D * p.z.T) + t; sstride = (int)p.z.T;
+        } else { goff = p.z.row_base(n); }
       }
-      if (rows > 0) {
-        load_rows(p.z, n0, rows, D, gtid, 128, [&](int r, int k, float v) {
-          const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-          const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-          const int off = r * 128 + (((k >> 3) ^ (r & 7)) << 4) + (k & 7) * 2;
-          *reinterpret_cast<__nv_bfloat16*>(a_hi + off) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(a_lo + off) = lo;
-        });
+      if (use_stage) { mbar_wait(smem_u32(sfull + rt), staged & 1, p.err, 8); ++staged; }
+      mbar_wait(smem_u32(aempty + rt), (tile_i & 1) ^ 1, p.err, 5);       // previous tile's MMAs are done with A
+      float xx = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = jj;                         // chunk j of 8 consecutive dims (A stores are conflict-free)
+        float v[8];
+        if (row < rows) {
+          if (p.stage_mode == STG_ROWS) {
+            const float4 f0 = *reinterpret_cast<const float4*>(src + j * 8);
+            const float4 f1 = *reinterpret_cast<const float4*>(src + j * 8 + 4);
+            v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w; v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
+          } else if (p.stage_mode == STG_BCT) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = src[(j * 8 + e) * sstride];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __ldg(p.z.p + goff + (long long)(j * 8 + e) * p.z.sC);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        }
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = v[2 * e], b = v[2 * e + 1];
+          xx = fmaf(a, a, xx); xx = fmaf(b, b, xx);
+          hw[e] = pack_bf16x2(a, b);
+          lw[e] = pack_bf16x2(a - __uint_as_float(hw[e] << 16), b - __uint_as_float(hw[e] & 0xFFFF0000u));
+        }
+        const int off = row * 128 + ((j ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       }
       fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core (async proxy)
       group_sync(1 + rt);
-      if (lane == 0) mbar_arrive(smem_u32(afull + rt));
-      // |x|^2 of this thread's row from the split operands (only feeds the error bound)
-      float xx = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int off = row * 128 + ((j ^ (row & 7)) << 4);
-        const uint4 h = *reinterpret_cast<const uint4*>(a_hi + off);
-        const uint4 l = *reinterpret_cast<const uint4*>(a_lo + off);
-        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float v0 = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
-          const float v1 = __uint_as_float(hw[e] & 0xFFFF0000u) + __uint_as_float(lw[e] & 0xFFFF0000u);
-          xx = fmaf(v0, v0, xx); xx = fmaf(v1, v1, xx);
-        }
+      if (lane == 0) {
+        mbar_arrive(smem_u32(afull + rt));
+        if (use_stage) mbar_arrive(smem_u32(sempty + rt));   // staging may be refilled for the NEXT tile now
       }
+      // ---- epilogue: running top-2 of s_k = x.E_k - |E_k|^2/2 over all code tiles ----
       float g1 = -INFINITY, g2 = -INFINITY; int gi = 0;
       for (int j = 0; j < NT; ++j, ++it) {
         const unsigned as = it & 1;
@@ -265,23 +343,28 @@ vq_assign_tc_kernel(const Params p) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * RT + rt) * BN);
         const float4* nh = reinterpret_cast<const float4*>(p.neg_half_ee + (size_t)j * BN);
         float t1 = -INFINITY, t2 = -INFINITY;
+        uint32_t va[32], vb[32];
+        tmem_ld32(taddr, va);
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
+          uint32_t (&cur)[32] = (c & 1) ? vb : va;
+          uint32_t (&nxt)[32] = (c & 1) ? va : vb;
           tmem_ld_wait();
+          if (c + 1 < BN / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);     // overlaps with the math below
 #pragma unroll
           for (int e4 = 0; e4 < 8; ++e4) {
             const float4 h = __ldg(nh + c * 8 + e4);
-            const float hv[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int col = c * 32 + e4 * 4 + e;
-              const float s = __uint_as_float(v[e4 * 4 + e]) + hv[e];
-              const float pk = __uint_as_float((__float_as_uint(s) & 0xFFFFFF80u) | (uint32_t)col);
-              t2 = fmaxf(t2, fminf(t1, pk));
-              t1 = fmaxf(t1, pk);
-            }
+            const int col = c * 32 + e4 * 4;
+            const float p0 = pack_col(__uint_as_float(cur[e4 * 4 + 0]) + h.x, col + 0, mask);
+            const float p1 = pack_col(__uint_as_float(cur[e4 * 4 + 1]) + h.y, col + 1, mask);
+            const float p2 = pack_col(__uint_as_float(cur[e4 * 4 + 2]) + h.z, col + 2, mask);
+            const float p3 = pack_col(__uint_as_float(cur[e4 * 4 + 3]) + h.w, col + 3, mask);
+            const float hi0 = fmaxf(p0, p1), lo0 = fminf(p0, p1);
+            t2 = fmax3(t2, lo0, fminf(t1, hi0));
+            t1 = fmaxf(t1, hi0);
+            const float hi1 = fmaxf(p2, p3), lo1 = fminf(p2, p3);
+            t2 = fmax3(t2, lo1, fminf(t1, hi1));
+            t1 = fmaxf(t1, hi1);
           }
         }
         tc_fence_before();
@@ -349,6 +432,16 @@ int launch_assign_tc(const ZView& z, const float* E, const float* ee, const void
   p.list = wsi + 64;
   p.list_count = wsi;
   p.err = wsi + 1;
+  // how the raw fp32 rows reach shared memory: one bulk-TMA copy per 128-row tile when the rows of a
+  // tile form one contiguous, 16-byte aligned byte range that fits the staging buffer
+  p.stage_mode = STG_DIRECT;
+  const bool aligned = (reinterpret_cast<uintptr_t>(z.p) & 15) == 0;
+  if (aligned && z.mode == Z_ROW && ((z.T == 1 && z.sB == D) || (z.sT == D && z.sB == z.T * D))) {
+    p.stage_mode = STG_ROWS;
+  } else if (aligned && z.mode == Z_BCT) {
+    const long long samples = (TILE_M - 1) / z.T + 2;            // most samples a 128-row tile can touch
+    if (samples * D * z.T * 4 <= STG_BYTES) p.stage_mode = STG_BCT;
+  }
   const int grid = (int)max(1LL, min(p.ntiles, (long long)sm_count()));
   vq_assign_tc_kernel<<<grid, NTHREADS, SMEM_TOTAL, stream>>>(p);
   VQ_LAUNCH_CHECK("vq_assign_tc_kernel");
