@@ -35,17 +35,18 @@ namespace tc {
 
 constexpr int RT = 2;                       // row tiles per CTA
 constexpr int TILE_M = 128;
-constexpr int BM = RT * TILE_M;             // 256 rows per CTA iteration
 constexpr int BN = IMG_TILE_CODES;          // 128 codes per accumulator
 constexpr int D = 64;
-constexpr int NST = 2;                      // codebook ring stages
+constexpr int NST = 3;                      // codebook ring stages
+constexpr int NHS = 5;                      // -|E|^2/2 ring slots (reuse distance NST+2, see producer)
 constexpr int A_HALF = TILE_M * 128;        // 16384 B: one of {hi, lo} for one row tile
 constexpr int SMEM_A = RT * 2 * A_HALF;     // 65536
-constexpr int STG_BYTES = 36864;            // raw fp32 z staging per row tile (bulk-TMA prefetched)
-constexpr int SMEM_STG = RT * STG_BYTES;    // 73728
-constexpr int SMEM_B = NST * IMG_TILE_BYTES;    // 65536
+constexpr int STG_BYTES = TILE_M * D * 4;   // 32768: raw fp32 z staging per row tile (bulk-TMA prefetched)
+constexpr int SMEM_STG = RT * STG_BYTES;    // 65536
+constexpr int SMEM_B = NST * IMG_TILE_BYTES;    // 98304
+constexpr int SMEM_NH = NHS * BN * 4;       // 2560
 constexpr int SMEM_BAR = 256;
-constexpr int SMEM_TOTAL = SMEM_A + SMEM_STG + SMEM_B + SMEM_BAR + 1024;   // + alignment slack
+constexpr int SMEM_TOTAL = SMEM_A + SMEM_STG + SMEM_B + SMEM_NH + SMEM_BAR;   // 232192 <= 232448
 enum StageMode : int { STG_DIRECT = 0, STG_ROWS = 1, STG_BCT = 2 };
 constexpr int NTHREADS = 320;
 constexpr unsigned SPIN_LIMIT = 1u << 22;   // bounded waits: a protocol bug traps instead of hanging the GPU
@@ -131,7 +132,8 @@ struct Params {
   const float* info;              // {max |E_k|, nonfinite flag}
   int K, NT;                      // codes, number of 128-code tiles
   int stage_mode;                 // how raw z reaches shared memory (StageMode)
-  long long ntiles;               // 256-row CTA tiles
+  int R;                          // rows per 4-warp group: 128, or the largest multiple of T <= 128 (whole samples)
+  long long ntiles;               // CTA tiles of 2*R rows
   int32_t* idx;
   int32_t* list;                  // rows that need the exact kernel
   int32_t* list_count;
@@ -144,12 +146,11 @@ __device__ __forceinline__ StagePlan stage_plan(const Params& p, long long n0, i
   StagePlan sp;
   if (p.stage_mode == STG_ROWS) {
     sp.src = p.z.p + n0 * D; sp.bytes = (uint32_t)rows * (D * 4); sp.b_lo = 0;
-  } else {
+  } else {                         // STG_BCT: groups start on sample boundaries and hold whole samples
     const long long T = p.z.T;
     sp.b_lo = n0 / T;
-    const long long b_hi = (n0 + rows - 1) / T;
     sp.src = p.z.p + sp.b_lo * (D * T);
-    sp.bytes = (uint32_t)((b_hi - sp.b_lo + 1) * (D * T * 4));
+    sp.bytes = (uint32_t)rows * (D * 4);
   }
   return sp;
 }
@@ -172,12 +173,12 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 vq_assign_tc_kernel(const Params p) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* sA = smem;                       // [RT][hi,lo][16384]
   unsigned char* sS = smem + SMEM_A;              // [RT][STG_BYTES]  raw fp32 staging
   unsigned char* sB = sS + SMEM_STG;              // [NST][32768]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SMEM_B);
+  float* sN = reinterpret_cast<float*>(sB + SMEM_B);          // [NHS][128]  -|E_k|^2/2 of in-flight code tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SMEM_B + SMEM_NH);
   uint64_t* full = bars;                 // [NST]      codebook tile landed
   uint64_t* empty = full + NST;          // [NST]      codebook tile consumed by the MMAs
   uint64_t* tfull = empty + NST;         // [2][RT]    accumulator ready
@@ -205,6 +206,9 @@ vq_assign_tc_kernel(const Params p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int NT = p.NT;
+  const int R = p.R;
+  const long long tile_rows = (long long)RT * R;
+  if ((smem_u32(smem) & 1023u) != 0u) { if (tid == 0 && p.err) atomicExch(p.err, 99); __trap(); }
 
   if (warp == 0) {
     // ================= bulk-TMA producer: raw z slabs + codebook tiles =================
@@ -214,8 +218,8 @@ vq_assign_tc_kernel(const Params p) {
         if (p.stage_mode != STG_DIRECT) {
 #pragma unroll
           for (int rt = 0; rt < RT; ++rt) {
-            const long long n0 = tile * BM + (long long)rt * TILE_M;
-            const int rows = (int)max(0LL, min((long long)TILE_M, p.z.N - n0));
+            const long long n0 = tile * tile_rows + (long long)rt * R;
+            const int rows = (int)max(0LL, min((long long)R, p.z.N - n0));
             if (rows > 0) {
               const StagePlan sp = stage_plan(p, n0, rows);
               mbar_wait(smem_u32(sempty + rt), (staged[rt] & 1) ^ 1, p.err, 7);
@@ -228,9 +232,12 @@ vq_assign_tc_kernel(const Params p) {
         for (int j = 0; j < NT; ++j, ++it) {
           const unsigned s = it % NST, ph = (it / NST) & 1;
           mbar_wait(smem_u32(empty + s), ph ^ 1, p.err, 1);
-          mbar_expect_tx(smem_u32(full + s), IMG_TILE_BYTES);
+          mbar_expect_tx(smem_u32(full + s), IMG_TILE_BYTES + BN * 4);
           bulk_g2s(smem_u32(sB + (size_t)s * IMG_TILE_BYTES), p.image + (size_t)j * IMG_TILE_BYTES, IMG_TILE_BYTES,
                    smem_u32(full + s));
+          // the epilogue of code tile `it` reads slot it % NHS until MMA(it+2) may start; this copy is issued
+          // after MMA(it+NHS-NST) = MMA(it+2) has completed, so the slot is free (NHS = NST + 2)
+          bulk_g2s(smem_u32(sN + (size_t)(it % NHS) * BN), p.neg_half_ee + (size_t)j * BN, BN * 4, smem_u32(full + s));
         }
       }
     }
@@ -279,8 +286,8 @@ vq_assign_tc_kernel(const Params p) {
     const uint32_t mask = 0xFFFFFF80u;
     unsigned it = 0, tile_i = 0, staged = 0;
     for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_i) {
-      const long long n0 = tile * BM + (long long)rt * TILE_M;
-      const int rows = (int)max(0LL, min((long long)TILE_M, p.z.N - n0));
+      const long long n0 = tile * tile_rows + (long long)rt * R;
+      const int rows = (int)max(0LL, min((long long)R, p.z.N - n0));
       const bool use_stage = (p.stage_mode != STG_DIRECT) && rows > 0;
       // ---- this thread's row: fp32 -> (hi, lo) bf16, swizzled K-major A operand; exact |x|^2 ----
       long long goff = 0; int sstride = 1; const float* src = nullptr;
@@ -339,9 +346,10 @@ vq_assign_tc_kernel(const Params p) {
       for (int j = 0; j < NT; ++j, ++it) {
         const unsigned as = it & 1;
         mbar_wait(smem_u32(tfull + as * RT + rt), (it >> 1) & 1, p.err, 6);
+        mbar_wait(smem_u32(full + it % NST), (it / NST) & 1, p.err, 9);    // acquire the bulk-copied -|E|^2/2 slot
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * RT + rt) * BN);
-        const float4* nh = reinterpret_cast<const float4*>(p.neg_half_ee + (size_t)j * BN);
+        const float4* nh = reinterpret_cast<const float4*>(sN + (size_t)(it % NHS) * BN);
         float t1 = -INFINITY, t2 = -INFINITY;
         uint32_t va[32], vb[32];
         tmem_ld32(taddr, va);
@@ -353,7 +361,7 @@ vq_assign_tc_kernel(const Params p) {
           if (c + 1 < BN / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);     // overlaps with the math below
 #pragma unroll
           for (int e4 = 0; e4 < 8; ++e4) {
-            const float4 h = __ldg(nh + c * 8 + e4);
+            const float4 h = nh[c * 8 + e4];
             const int col = c * 32 + e4 * 4;
             const float p0 = pack_col(__uint_as_float(cur[e4 * 4 + 0]) + h.x, col + 0, mask);
             const float p1 = pack_col(__uint_as_float(cur[e4 * 4 + 1]) + h.y, col + 1, mask);
@@ -427,7 +435,6 @@ int launch_assign_tc(const ZView& z, const float* E, const float* ee, const void
   p.info = info;
   p.K = K;
   p.NT = (int)(img_kp(K) / IMG_TILE_CODES);
-  p.ntiles = (z.N + BM - 1) / BM;
   p.idx = idx;
   p.list = wsi + 64;
   p.list_count = wsi;
@@ -435,13 +442,15 @@ int launch_assign_tc(const ZView& z, const float* E, const float* ee, const void
   // how the raw fp32 rows reach shared memory: one bulk-TMA copy per 128-row tile when the rows of a
   // tile form one contiguous, 16-byte aligned byte range that fits the staging buffer
   p.stage_mode = STG_DIRECT;
+  p.R = TILE_M;
   const bool aligned = (reinterpret_cast<uintptr_t>(z.p) & 15) == 0;
   if (aligned && z.mode == Z_ROW && ((z.T == 1 && z.sB == D) || (z.sT == D && z.sB == z.T * D))) {
     p.stage_mode = STG_ROWS;
-  } else if (aligned && z.mode == Z_BCT) {
-    const long long samples = (TILE_M - 1) / z.T + 2;            // most samples a 128-row tile can touch
-    if (samples * D * z.T * 4 <= STG_BYTES) p.stage_mode = STG_BCT;
+  } else if (aligned && z.mode == Z_BCT && z.T <= TILE_M) {
+    p.stage_mode = STG_BCT;                                     // whole samples per group: R = floor(128/T)*T
+    p.R = (int)((TILE_M / z.T) * z.T);
   }
+  p.ntiles = (z.N + (long long)RT * p.R - 1) / ((long long)RT * p.R);
   const int grid = (int)max(1LL, min(p.ntiles, (long long)sm_count()));
   vq_assign_tc_kernel<<<grid, NTHREADS, SMEM_TOTAL, stream>>>(p);
   VQ_LAUNCH_CHECK("vq_assign_tc_kernel");
