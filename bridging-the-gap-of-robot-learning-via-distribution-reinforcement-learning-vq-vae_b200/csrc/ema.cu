@@ -5,6 +5,9 @@
 
 namespace vqb200 {
 
+int try_accumulate_tile(const ZView& z, const int32_t* idx, const float* E, int K, float* dw, float* cnt, int mode,
+                        cudaStream_t stream);
+
 // ------------------------------------------------------------------------------------------
 // codebook_prepare: ee[k] = sum_c E[k,c]^2, bf16 tile image, info.
 // one warp per code row.
@@ -237,6 +240,10 @@ int vqb200_ema_accumulate(const float* z, int64_t B, int64_t C, int64_t T, int64
   VQ_CUDA(cudaMemsetAsync(stats, 0, (size_t)K * (D + 1) * sizeof(float), stream));
   if (B * T == 0) return VQB200_OK;
   const ZView zv = make_zview(z, B, C, T, sB, sC, sT);
+  {
+    const int rc = try_accumulate_tile(zv, idx, E, (int)K, dw, cnt, mode, stream);
+    if (rc != 0) return rc == 1 ? VQB200_OK : rc;
+  }
   const int use_hist = (K <= ACC_HIST_MAX) ? 1 : 0;
   const size_t smem = (size_t)ACC_BM * (D + 4) * sizeof(float) + (use_hist ? (size_t)K * sizeof(int) : 0);
   VQ_CHECK_ARG(smem <= 227 * 1024, VQB200_ESHAPE, "ema_accumulate: D=%d K=%lld needs %zu B of shared memory", D, (long long)K, smem);

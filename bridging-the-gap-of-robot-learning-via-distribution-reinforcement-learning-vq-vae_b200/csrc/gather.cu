@@ -5,6 +5,10 @@
 
 namespace vqb200 {
 
+int try_gather_tile(const ZView& z, const float* E, const int32_t* idx, int K, int mode, float* o1, float* o2,
+                    const float* in2, int accum_init, const float* g_loss, float coef, double* sse,
+                    cudaStream_t stream);
+
 struct Decomp { long long b; int c, t; };
 
 __device__ __forceinline__ Decomp decomp(long long i, int C, int T, long long CT) {
@@ -117,6 +121,12 @@ int vqb200_vq_gather_st(const float* z, int64_t B, int64_t C, int64_t T, int64_t
   const long long total = B * C * T;
   if (total == 0) return VQB200_OK;
   const ZView zv = make_zview(z, B, C, T, sB, sC, sT);
+  // contiguous layouts: coalesced row-tile kernel (tile_ops.cu); arbitrary views: generic strided kernel
+  if (!(out && (residual || accum))) {
+    const int rc = out ? try_gather_tile(zv, E, idx, (int)K, 0, out, nullptr, nullptr, 0, nullptr, 0.f, sse, stream)
+                       : try_gather_tile(zv, E, idx, (int)K, 1, residual, accum, nullptr, accum_init, nullptr, 0.f, sse, stream);
+    if (rc != 0) return rc == 1 ? VQB200_OK : rc;
+  }
   gather_st_kernel<<<grid_for(total, 256 * 4, sm_count() * 8), 256, 0, stream>>>(zv, E, idx, (int)K, out, residual,
                                                                                accum, accum_init, sse);
   VQ_LAUNCH_CHECK("gather_st_kernel");
@@ -143,6 +153,10 @@ int vqb200_vq_backward_input(const float* g, int64_t gsB, int64_t gsC, int64_t g
   const long long total = B * C * T;
   if (total == 0) return VQB200_OK;
   const ZView zv = make_zview(z, B, C, T, sB, sC, sT);
+  if (!g || (gsT == 1 && gsC == T && gsB == C * T) || (T == 1 && gsC == 1 && gsB == C)) {   // g laid out like gz
+    const int rc = try_gather_tile(zv, E, idx, (int)K, 2, gz, nullptr, g, 0, g_loss, coef, nullptr, stream);
+    if (rc != 0) return rc == 1 ? VQB200_OK : rc;
+  }
   backward_input_kernel<<<grid_for(total, 256 * 4, sm_count() * 8), 256, 0, stream>>>(g, gsB, gsC, gsT, zv, E, idx,
                                                                                     (int)K, g_loss, coef, gz);
   VQ_LAUNCH_CHECK("backward_input_kernel");

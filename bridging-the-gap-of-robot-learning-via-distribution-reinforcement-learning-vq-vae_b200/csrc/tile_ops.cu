@@ -1,0 +1,213 @@
+// vqb200 -- HBM-bound row-tile kernels for the contiguous layouts ([B,C,T] contiguous, or [N,D] rows).
+//
+// A tile is a run of WHOLE samples, i.e. one contiguous byte range of the tensor, so every global access
+// is a coalesced 16-byte stream; the channel-major <-> row transposition happens in shared memory:
+//   1. stream the tile (and the second operand: running RVQ sum or upstream gradient) into smem,
+//   2. walk it row-wise (lanes along the channel dim: codeword rows E[idx] are read as coalesced
+//      128-byte lines, smem is read with stride T -- at most 2-way bank conflicts for even T),
+//   3. stream the results back.
+// Used by vq_gather_st (K2), vq_backward_input (K2b) and ema_accumulate (K3a); the generic strided
+// kernels in gather.cu / ema.cu remain the fallback for arbitrary views.
+#include "common.cuh"
+
+namespace vqb200 {
+
+constexpr int TILE_ELEMS = 4096;          // gather / backward: 16 KiB per tile buffer (small tiles -> many CTAs per SM)
+constexpr int ACC_TILE_ELEMS = 8192;      // accumulate: 32 KiB tiles (fewer histogram flushes)
+constexpr int TILE_NT = 256;
+
+struct TileGeom {
+  int D, T;              // channels, time steps (T == 1 for row-major [N,D])
+  int rows_per_tile;     // multiple of T
+  int dshift;            // log2(D) if D is a power of two, else -1
+  long long N;           // total rows
+  long long ntiles;
+};
+
+inline bool tile_geom(const ZView& z, TileGeom& g, int tile_elems = TILE_ELEMS) {
+  const bool rows_contig = z.mode == Z_ROW && z.T == 1 && z.sB == z.C;
+  const bool bct = z.mode == Z_BCT;
+  if (!rows_contig && !bct) return false;
+  if ((z.C & 3) || (reinterpret_cast<uintptr_t>(z.p) & 15)) return false;
+  const long long slab = z.C * z.T;
+  if (slab > tile_elems || slab <= 0) return false;
+  g.D = (int)z.C; g.T = (int)z.T;
+  if (z.T > 256) return false;
+  g.rows_per_tile = (int)min((tile_elems / slab) * z.T, (256 / z.T) * z.T);
+  g.dshift = -1;
+  for (int sh = 0; sh < 16; ++sh) if ((1 << sh) == g.D) g.dshift = sh;
+  g.N = z.N;
+  g.ntiles = (z.N + g.rows_per_tile - 1) / g.rows_per_tile;
+  return true;
+}
+
+__device__ __forceinline__ void tile_copy_in(float* dst, const float* __restrict__ src, int n, int tid) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (int i = tid; i < (n >> 2); i += TILE_NT) d4[i] = __ldg(s4 + i);
+}
+__device__ __forceinline__ void tile_copy_out(float* __restrict__ dst, const float* src, int n, int tid) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (int i = tid; i < (n >> 2); i += TILE_NT) d4[i] = s4[i];
+}
+
+enum GatherMode : int { GM_PLAIN = 0, GM_RVQ = 1, GM_BACKWARD = 2 };
+
+// GM_PLAIN   : o1[...] = x + (q - x)                                   (out)
+// GM_RVQ     : o1[...] = x - st (next residual, optional), o2 = (init ? o2 : 0) + st   (running sum)
+// GM_BACKWARD: o1[...] = in2 + scale*(x - q)                           (in2 = upstream gradient, may be null)
+__global__ void __launch_bounds__(TILE_NT)
+gather_tile_kernel(const float* __restrict__ z, const float* __restrict__ E, const int32_t* __restrict__ idx,
+                   int K, TileGeom g, int mode, float* __restrict__ o1, float* __restrict__ o2,
+                   const float* __restrict__ in2, int accum_init, const float* __restrict__ g_loss, float coef,
+                   double* __restrict__ sse) {
+  extern __shared__ __align__(16) float smem[];
+  float* X = smem;                               // [TILE_ELEMS]
+  float* Y = smem + TILE_ELEMS;                  // [TILE_ELEMS] second operand / second result
+  __shared__ int s_off[256];
+  __shared__ int s_code[256];
+  const int tid = threadIdx.x;
+  const int D = g.D, T = g.T;
+  const float scale = (mode == GM_BACKWARD) ? __fmul_rn(g_loss ? __ldg(g_loss) : 1.0f, coef) : 0.f;
+  const bool need_y_in = (mode == GM_RVQ && o2 && accum_init) || (mode == GM_BACKWARD && in2);
+  float part = 0.f;
+  for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+    const long long r0 = tile * g.rows_per_tile;
+    const int rows = (int)min((long long)g.rows_per_tile, g.N - r0);
+    const int n = rows * D;
+    const long long e0 = r0 * D;                 // whole samples: element offset of the tile
+    __syncthreads();
+    tile_copy_in(X, z + e0, n, tid);
+    if (need_y_in) tile_copy_in(Y, (mode == GM_BACKWARD ? in2 : o2) + e0, n, tid);
+    if (tid < rows) {
+      const int b = tid / T, t = tid - b * T;
+      s_off[tid] = b * D * T + t;
+      int k = __ldg(idx + r0 + tid);
+      s_code[tid] = min(max(k, 0), K - 1);
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += TILE_NT) {
+      const int r = g.dshift >= 0 ? (i >> g.dshift) : (i / D);
+      const int k = i - r * D;
+      const int a = s_off[r] + k * T;
+      const float x = X[a];
+      const float q = __ldg(E + (size_t)s_code[r] * D + k);
+      if (mode == GM_BACKWARD) {
+        X[a] = fmaf(scale, __fsub_rn(x, q), need_y_in ? Y[a] : 0.f);
+      } else {
+        const float diff = __fsub_rn(q, x);
+        const float st = __fadd_rn(x, diff);
+        part = fmaf(diff, diff, part);
+        if (mode == GM_PLAIN) X[a] = st;
+        else {
+          X[a] = __fsub_rn(x, st);
+          Y[a] = __fadd_rn(need_y_in ? Y[a] : 0.f, st);
+        }
+      }
+    }
+    __syncthreads();
+    if (o1) tile_copy_out(o1 + e0, X, n, tid);
+    if (mode == GM_RVQ && o2) tile_copy_out(o2 + e0, Y, n, tid);
+  }
+  if (sse) {
+    __shared__ double red[TILE_NT / 32];
+    double p = warp_sum((double)part);
+    if ((tid & 31) == 0) red[tid >> 5] = p;
+    __syncthreads();
+    if (tid < 32) {
+      double v = tid < TILE_NT / 32 ? red[tid] : 0.0;
+      v = warp_sum(v);
+      if (tid == 0 && v != 0.0) atomicAdd(sse, v);
+    }
+  }
+}
+
+// ema_accumulate on a tile: cnt via smem histogram, dw via 16-byte vector reductions
+__global__ void __launch_bounds__(TILE_NT)
+accumulate_tile_kernel(const float* __restrict__ z, const int32_t* __restrict__ idx, const float* __restrict__ E,
+                       int K, TileGeom g, float* __restrict__ dw, float* __restrict__ cnt, int mode, int use_hist) {
+  extern __shared__ __align__(16) float smem[];
+  float* X = smem;
+  int* hist = reinterpret_cast<int*>(smem + ACC_TILE_ELEMS);
+  __shared__ int s_off[256];
+  __shared__ int s_code[256];
+  const int tid = threadIdx.x;
+  const int D = g.D, T = g.T, d4 = D >> 2;
+  if (use_hist) for (int k = tid; k < K; k += TILE_NT) hist[k] = 0;
+  for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+    const long long r0 = tile * g.rows_per_tile;
+    const int rows = (int)min((long long)g.rows_per_tile, g.N - r0);
+    const int n = rows * D;
+    __syncthreads();
+    tile_copy_in(X, z + r0 * D, n, tid);
+    if (tid < rows) {
+      const int b = tid / T, t = tid - b * T;
+      s_off[tid] = b * D * T + t;
+      const int k = __ldg(idx + r0 + tid);
+      s_code[tid] = k;
+      if ((unsigned)k < (unsigned)K) { if (use_hist) atomicAdd(hist + k, 1); else atomicAdd(cnt + k, 1.0f); }
+    }
+    __syncthreads();
+    for (int i = tid; i < rows * d4; i += TILE_NT) {
+      const int r = i / d4, q = i - r * d4;
+      const int k = s_code[r];
+      if ((unsigned)k >= (unsigned)K) continue;
+      const int a = s_off[r] + 4 * q * T;
+      float4 v = make_float4(X[a], X[a + T], X[a + 2 * T], X[a + 3 * T]);
+      if (mode == 1) {
+        const float4 e = __ldg(reinterpret_cast<const float4*>(E + (size_t)k * D) + q);
+        v = make_float4(e.x - v.x, e.y - v.y, e.z - v.z, e.w - v.w);
+      }
+      red_add_v4(dw + (size_t)k * D + 4 * q, v.x, v.y, v.z, v.w);
+    }
+  }
+  if (use_hist) {
+    __syncthreads();
+    for (int k = tid; k < K; k += TILE_NT) { const int h = hist[k]; if (h) atomicAdd(cnt + k, (float)h); }
+  }
+}
+
+static int tile_grid(const TileGeom& g, int per_sm) {
+  return (int)max(1LL, min(g.ntiles, (long long)sm_count() * per_sm));
+}
+
+// returns 1 if handled, 0 if the layout is not eligible (caller falls back), < 0 / > 0 on error
+int try_gather_tile(const ZView& z, const float* E, const int32_t* idx, int K, int mode, float* o1, float* o2,
+                    const float* in2, int accum_init, const float* g_loss, float coef, double* sse,
+                    cudaStream_t stream) {
+  TileGeom g;
+  if (!tile_geom(z, g)) return 0;
+  if ((reinterpret_cast<uintptr_t>(o1) & 15) || (reinterpret_cast<uintptr_t>(o2) & 15) ||
+      (reinterpret_cast<uintptr_t>(in2) & 15) || (reinterpret_cast<uintptr_t>(E) & 3)) return 0;
+  const bool two = (mode == GM_RVQ) || (mode == GM_BACKWARD && in2);
+  const size_t smem = (two ? 2 : 1) * TILE_ELEMS * sizeof(float);
+  gather_tile_kernel<<<tile_grid(g, 8), TILE_NT, smem, stream>>>(z.p, E, idx, K, g, mode, o1, o2, in2, accum_init,
+                                                                g_loss, coef, sse);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "gather_tile_kernel");
+  return 1;
+}
+
+int try_accumulate_tile(const ZView& z, const int32_t* idx, const float* E, int K, float* dw, float* cnt, int mode,
+                        cudaStream_t stream) {
+  TileGeom g;
+  if (!tile_geom(z, g, ACC_TILE_ELEMS)) return 0;
+  if ((reinterpret_cast<uintptr_t>(dw) & 15) || (mode == 1 && (reinterpret_cast<uintptr_t>(E) & 15))) return 0;
+  const int use_hist = K <= 8192 ? 1 : 0;
+  const size_t smem = ACC_TILE_ELEMS * sizeof(float) + (use_hist ? (size_t)K * sizeof(int) : 0);
+  static thread_local size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(accumulate_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(accumulate_tile_kernel)");
+    configured = smem;
+  }
+  accumulate_tile_kernel<<<tile_grid(g, 4), TILE_NT, smem, stream>>>(z.p, idx, E, K, g, dw, cnt, mode, use_hist);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "accumulate_tile_kernel");
+  return 1;
+}
+
+}  // namespace vqb200

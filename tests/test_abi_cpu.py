@@ -35,9 +35,9 @@ def test_library_exports_every_declared_symbol():
 def test_size_queries_need_no_gpu():
     import vqb200
     lib = vqb200._lib.load()
-    # 1024 x 64 bf16 = 4 tiles of 32 KiB + 1024 fp32 norms
-    assert lib.vqb200_codebook_image_bytes(1024, 64) == 4 * 32768 + 1024 * 4
-    assert lib.vqb200_codebook_image_bytes(1000, 24) == 4 * 32768 + 1024 * 4
+    # 1024 x 64 split-bf16 image = 8 code tiles x (16 KiB hi + 16 KiB lo) + 1024 fp32 values of -|E|^2/2
+    assert lib.vqb200_codebook_image_bytes(1024, 64) == 8 * 32768 + 1024 * 4
+    assert lib.vqb200_codebook_image_bytes(1000, 24) == 8 * 32768 + 1024 * 4
     assert lib.vqb200_unique_workspace_bytes() > 256 * 1024
     assert lib.vqb200_assign_workspace_bytes(1000) >= 1000 * 4
 
