@@ -13,15 +13,20 @@
 //   index packing).  Rows that cannot be proven (near-ties, non-finite data) are appended to a work
 //   list and re-done by the exact fp32 CUDA-core kernel (assign_simt.cu) -- typically < 1 % of rows.
 //
-// Structure (one persistent CTA per SM, 320 threads):
-//   warp 0      bulk-TMA producer: streams 32 KiB codebook tiles (E_hi | E_lo, pre-swizzled image
-//               written by ema_finalize / codebook_prepare) through a 4-stage mbarrier ring
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=128, K=16, kind::f16)
-//   warps 2-9   two groups of 4 warps, one 128-row tile each: load + split z into swizzled smem
-//               A operands, then tcgen05.ld the fp32 scores (one row per thread) and run the
-//               running top-2 with the code index packed into the low mantissa bits.
+// Structure (one persistent CTA per SM, 448 threads, every hand-off through mbarriers):
+//   warp 0       bulk-TMA producer: (a) prefetches the NEXT tile's raw fp32 rows (one contiguous slab
+//                per 128-row group) into a ping-pong buffer, (b) streams 32 KiB codebook tiles
+//                (E_hi | E_lo, pre-swizzled image written by ema_finalize / codebook_prepare) plus
+//                their 512 B of -|E|^2/2 through a 3-stage ring
+//   warp 1       TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=128, K=16, kind::f16)
+//   warps 2-9    epilogue: two groups of 4 warps, one 128-row tile each; tcgen05.ld the fp32 scores
+//                (one row per thread, software-pipelined) and run the running top-2 with the code
+//                index packed into the low mantissa bits (3.5 ALU ops per score)
+//   warps 10-13  converter: turns the prefetched raw rows IN PLACE into the swizzled K-major split-bf16
+//                A operands of the next tile while the epilogue warps are still busy with this one
 //   TMEM: 4 accumulators of 128 columns (2 row tiles x 2 stages) = all 512 columns, so the MMAs of
 //   code tile j+1 overlap the epilogue of code tile j.
+#include <stdlib.h>
 #include "common.cuh"
 #include "codebook.cuh"
 
@@ -40,15 +45,14 @@ constexpr int D = 64;
 constexpr int NST = 3;                      // codebook ring stages
 constexpr int NHS = 5;                      // -|E|^2/2 ring slots (reuse distance NST+2, see producer)
 constexpr int A_HALF = TILE_M * 128;        // 16384 B: one of {hi, lo} for one row tile
-constexpr int SMEM_A = RT * 2 * A_HALF;     // 65536
-constexpr int STG_BYTES = TILE_M * D * 4;   // 32768: raw fp32 z staging per row tile (bulk-TMA prefetched)
-constexpr int SMEM_STG = RT * STG_BYTES;    // 65536
+constexpr int BUF_BYTES = 2 * A_HALF;       // 32768: raw fp32 rows, converted in place to [hi | lo]
+constexpr int SMEM_BUF = RT * 2 * BUF_BYTES;    // 131072: ping-pong per row tile
 constexpr int SMEM_B = NST * IMG_TILE_BYTES;    // 98304
 constexpr int SMEM_NH = NHS * BN * 4;       // 2560
 constexpr int SMEM_BAR = 256;
-constexpr int SMEM_TOTAL = SMEM_A + SMEM_STG + SMEM_B + SMEM_NH + SMEM_BAR;   // 232192 <= 232448
+constexpr int SMEM_TOTAL = SMEM_BUF + SMEM_B + SMEM_NH + SMEM_BAR;   // 232192 <= 232448
 enum StageMode : int { STG_DIRECT = 0, STG_ROWS = 1, STG_BCT = 2 };
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS = 448;
 constexpr unsigned SPIN_LIMIT = 1u << 22;   // bounded waits: a protocol bug traps instead of hanging the GPU
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -110,7 +114,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" :: "r"(id) : "memory"); }
+__device__ __forceinline__ void converter_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 128-byte rows, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
@@ -138,19 +142,19 @@ struct Params {
   int32_t* list;                  // rows that need the exact kernel
   int32_t* list_count;
   int* err;
+  int dbg;                        // development knobs (VQB200_TC_DEBUG): 1 = skip epilogue math, 2 = one k-block
 };
 
 // Byte range of the raw fp32 input that covers rows [n0, n0+rows) (staged modes only).
 struct StagePlan { const float* src; uint32_t bytes; long long b_lo; };
 __device__ __forceinline__ StagePlan stage_plan(const Params& p, long long n0, int rows) {
   StagePlan sp;
+  sp.bytes = (uint32_t)rows * (D * 4);
   if (p.stage_mode == STG_ROWS) {
-    sp.src = p.z.p + n0 * D; sp.bytes = (uint32_t)rows * (D * 4); sp.b_lo = 0;
+    sp.src = p.z.p + n0 * D; sp.b_lo = 0;
   } else {                         // STG_BCT: groups start on sample boundaries and hold whole samples
-    const long long T = p.z.T;
-    sp.b_lo = n0 / T;
-    sp.src = p.z.p + sp.b_lo * (D * T);
-    sp.bytes = (uint32_t)rows * (D * 4);
+    sp.b_lo = n0 / p.z.T;
+    sp.src = p.z.p + sp.b_lo * (D * p.z.T);
   }
   return sp;
 }
@@ -174,29 +178,28 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 __global__ void __launch_bounds__(NTHREADS, 1)
 vq_assign_tc_kernel(const Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* sA = smem;                       // [RT][hi,lo][16384]
-  unsigned char* sS = smem + SMEM_A;              // [RT][STG_BYTES]  raw fp32 staging
-  unsigned char* sB = sS + SMEM_STG;              // [NST][32768]
+  unsigned char* sBuf = smem;                     // [RT][2][32768]  raw rows -> A operands (in place)
+  unsigned char* sB = smem + SMEM_BUF;            // [NST][32768]    codebook tiles
   float* sN = reinterpret_cast<float*>(sB + SMEM_B);          // [NHS][128]  -|E_k|^2/2 of in-flight code tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + SMEM_B + SMEM_NH);
-  uint64_t* full = bars;                 // [NST]      codebook tile landed
-  uint64_t* empty = full + NST;          // [NST]      codebook tile consumed by the MMAs
-  uint64_t* tfull = empty + NST;         // [2][RT]    accumulator ready
-  uint64_t* tempty = tfull + 2 * RT;     // [2][RT]    accumulator drained
-  uint64_t* afull = tempty + 2 * RT;     // [RT]       A operands written
-  uint64_t* aempty = afull + RT;         // [RT]       A operands no longer read
-  uint64_t* sfull = aempty + RT;         // [RT]       raw z staged
-  uint64_t* sempty = sfull + RT;         // [RT]       staging consumed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + RT);
+  uint64_t* full = bars;                 // [NST]        codebook tile landed
+  uint64_t* empty = full + NST;          // [NST]        codebook tile consumed by the MMAs
+  uint64_t* tfull = empty + NST;         // [2][RT]      accumulator ready
+  uint64_t* tempty = tfull + 2 * RT;     // [2][RT]      accumulator drained
+  uint64_t* rawfull = tempty + 2 * RT;   // [RT][2]      raw rows landed in the ping-pong buffer
+  uint64_t* afull = rawfull + 2 * RT;    // [RT][2]      A operands written
+  uint64_t* aempty = afull + 2 * RT;     // [RT][2]      A operands no longer read by the tensor core
+  uint64_t* nhfull = aempty + 2 * RT;    // [NHS]        -|E|^2/2 slot landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(nhfull + NHS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
-    for (int i = 0; i < 2 * RT; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4); }
-    for (int r = 0; r < RT; ++r) {
-      mbar_init(smem_u32(afull + r), 4); mbar_init(smem_u32(aempty + r), 1);
-      mbar_init(smem_u32(sfull + r), 1); mbar_init(smem_u32(sempty + r), 4);
+    for (int s = 0; s < NHS; ++s) mbar_init(smem_u32(nhfull + s), 1);
+    for (int i = 0; i < 2 * RT; ++i) {
+      mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4);
+      mbar_init(smem_u32(rawfull + i), 1); mbar_init(smem_u32(afull + i), 4); mbar_init(smem_u32(aempty + i), 1);
     }
     fence_barrier_init();
   }
@@ -209,35 +212,43 @@ vq_assign_tc_kernel(const Params p) {
   const int R = p.R;
   const long long tile_rows = (long long)RT * R;
   if ((smem_u32(smem) & 1023u) != 0u) { if (tid == 0 && p.err) atomicExch(p.err, 99); __trap(); }
+  const bool staged = p.stage_mode != STG_DIRECT;
 
   if (warp == 0) {
-    // ================= bulk-TMA producer: raw z slabs + codebook tiles =================
+    // ================= bulk-TMA producer: raw z slabs (one tile ahead) + codebook tiles =================
     if (lane == 0) {
-      unsigned it = 0, staged[RT] = {0, 0};
-      for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        if (p.stage_mode != STG_DIRECT) {
+      auto issue_raw = [&](long long tile, unsigned tile_i) {
+        if (!staged || tile >= p.ntiles) return;
+        const unsigned pp = tile_i & 1, u = tile_i >> 1;
 #pragma unroll
-          for (int rt = 0; rt < RT; ++rt) {
-            const long long n0 = tile * tile_rows + (long long)rt * R;
-            const int rows = (int)max(0LL, min((long long)R, p.z.N - n0));
-            if (rows > 0) {
-              const StagePlan sp = stage_plan(p, n0, rows);
-              mbar_wait(smem_u32(sempty + rt), (staged[rt] & 1) ^ 1, p.err, 7);
-              mbar_expect_tx(smem_u32(sfull + rt), sp.bytes);
-              bulk_g2s(smem_u32(sS + (size_t)rt * STG_BYTES), sp.src, sp.bytes, smem_u32(sfull + rt));
-              ++staged[rt];
-            }
+        for (int rt = 0; rt < RT; ++rt) {
+          const long long n0 = tile * tile_rows + (long long)rt * R;
+          const int rows = (int)max(0LL, min((long long)R, p.z.N - n0));
+          if (rows > 0) {
+            const StagePlan sp = stage_plan(p, n0, rows);
+            mbar_wait(smem_u32(aempty + rt * 2 + pp), (u & 1) ^ 1, p.err, 7);     // MMAs of tile_i-2 left the buffer
+            mbar_expect_tx(smem_u32(rawfull + rt * 2 + pp), sp.bytes);
+            bulk_g2s(smem_u32(sBuf + (size_t)(rt * 2 + pp) * BUF_BYTES), sp.src, sp.bytes, smem_u32(rawfull + rt * 2 + pp));
           }
         }
+      };
+      unsigned it = 0, tile_i = 0;
+      issue_raw(blockIdx.x, 0);
+      const int j_raw = min(NST, NT - 1);         // by then the MMAs of the previous tile are done
+      for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_i) {
         for (int j = 0; j < NT; ++j, ++it) {
           const unsigned s = it % NST, ph = (it / NST) & 1;
           mbar_wait(smem_u32(empty + s), ph ^ 1, p.err, 1);
-          mbar_expect_tx(smem_u32(full + s), IMG_TILE_BYTES + BN * 4);
+          if (j == j_raw) issue_raw(tile + gridDim.x, tile_i + 1);
+          mbar_expect_tx(smem_u32(full + s), IMG_TILE_BYTES);
           bulk_g2s(smem_u32(sB + (size_t)s * IMG_TILE_BYTES), p.image + (size_t)j * IMG_TILE_BYTES, IMG_TILE_BYTES,
                    smem_u32(full + s));
           // the epilogue of code tile `it` reads slot it % NHS until MMA(it+2) may start; this copy is issued
-          // after MMA(it+NHS-NST) = MMA(it+2) has completed, so the slot is free (NHS = NST + 2)
-          bulk_g2s(smem_u32(sN + (size_t)(it % NHS) * BN), p.neg_half_ee + (size_t)j * BN, BN * 4, smem_u32(full + s));
+          // after MMA(it+NHS-NST) = MMA(it+2) has completed, so the slot is free AND its barrier cannot run a
+          // phase ahead of the epilogue's parity wait (NHS = NST + 2)
+          mbar_expect_tx(smem_u32(nhfull + it % NHS), BN * 4);
+          bulk_g2s(smem_u32(sN + (size_t)(it % NHS) * BN), p.neg_half_ee + (size_t)j * BN, BN * 4,
+                   smem_u32(nhfull + it % NHS));
         }
       }
     }
@@ -246,6 +257,7 @@ vq_assign_tc_kernel(const Params p) {
     if (lane == 0) {
       unsigned it = 0, tile_i = 0;
       for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_i) {
+        const unsigned pp = tile_i & 1, u = tile_i >> 1;
         for (int j = 0; j < NT; ++j, ++it) {
           const unsigned s = it % NST, as = it & 1;
           mbar_wait(smem_u32(full + s), (it / NST) & 1, p.err, 2);
@@ -253,13 +265,14 @@ vq_assign_tc_kernel(const Params p) {
           const uint32_t b_hi = smem_u32(sB + (size_t)s * IMG_TILE_BYTES), b_lo = b_hi + IMG_HALF_BYTES;
 #pragma unroll
           for (int rt = 0; rt < RT; ++rt) {
-            if (j == 0) mbar_wait(smem_u32(afull + rt), tile_i & 1, p.err, 3);
+            if (j == 0) mbar_wait(smem_u32(afull + rt * 2 + pp), u & 1, p.err, 3);
             mbar_wait(smem_u32(tempty + as * RT + rt), ((it >> 1) & 1) ^ 1, p.err, 4);
             tc_fence_after();
-            const uint32_t a_hi = smem_u32(sA + (size_t)rt * 2 * A_HALF), a_lo = a_hi + A_HALF;
+            const uint32_t a_hi = smem_u32(sBuf + (size_t)(rt * 2 + pp) * BUF_BYTES), a_lo = a_hi + A_HALF;
             const uint32_t d_tmem = tmem_base + (uint32_t)((as * RT + rt) * BN);
 #pragma unroll
-            for (int kb = 0; kb < 3; ++kb) {            // x_hi.E_hi + x_lo.E_hi + x_hi.E_lo
+            const int nkb = (p.dbg & 2) ? 1 : 3;
+            for (int kb = 0; kb < nkb; ++kb) {          // x_hi.E_hi + x_lo.E_hi + x_hi.E_lo
               const uint32_t a = (kb == 1) ? a_lo : a_hi;
               const uint32_t b = (kb == 2) ? b_lo : b_hi;
 #pragma unroll
@@ -267,86 +280,106 @@ vq_assign_tc_kernel(const Params p) {
                 umma_bf16(d_tmem, umma_desc(a + k * 32), umma_desc(b + k * 32), IDESC, (kb | k) ? 1u : 0u);
             }
             umma_commit(smem_u32(tfull + as * RT + rt));
-            if (j == NT - 1) umma_commit(smem_u32(aempty + rt));
+            if (j == NT - 1) umma_commit(smem_u32(aempty + rt * 2 + pp));
           }
           umma_commit(smem_u32(empty + s));
         }
       }
     }
-  } else {
-    // ================= converter + epilogue groups (4 warps = 128 rows each) =================
-    const int rt = (warp - 2) >> 2;
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;                // accumulator lane == row inside the row tile
-    unsigned char* a_hi = sA + (size_t)rt * 2 * A_HALF;
-    unsigned char* a_lo = a_hi + A_HALF;
-    const float* stg = reinterpret_cast<const float*>(sS + (size_t)rt * STG_BYTES);
-    const float emax = p.info[0];
-    const bool cb_bad = p.info[1] != 0.f;
-    const uint32_t mask = 0xFFFFFF80u;
-    unsigned it = 0, tile_i = 0, staged = 0;
+  } else if (warp >= 10) {
+    // ================= converter: raw fp32 rows -> swizzled split-bf16 A operands, in place =================
+    const int row = (warp - 10) * 32 + lane;      // 0..127: this thread's row inside the group
+    unsigned tile_i = 0;
     for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_i) {
-      const long long n0 = tile * tile_rows + (long long)rt * R;
-      const int rows = (int)max(0LL, min((long long)R, p.z.N - n0));
-      const bool use_stage = (p.stage_mode != STG_DIRECT) && rows > 0;
-      // ---- this thread's row: fp32 -> (hi, lo) bf16, swizzled K-major A operand; exact |x|^2 ----
-      long long goff = 0; int sstride = 1; const float* src = nullptr;
-      if (row < rows) {
-        const long long n = n0 + row;
-        if (p.stage_mode == STG_ROWS) { src = stg + row * D; sstride = 1; }
-        else if (p.stage_mode == STG_BCT) {
-          const StagePlan sp = stage_plan(p, n0, rows);
-          const long long b = n / p.z.T; const int t = (int)(n - b * p.z.T);
-          src = stg + (b - sp.b_lo) * (D * p.z.T) + t; sstride = (int)p.z.T;
-        } else { goff = p.z.row_base(n); }
-      }
-      if (use_stage) { mbar_wait(smem_u32(sfull + rt), staged & 1, p.err, 8); ++staged; }
-      mbar_wait(smem_u32(aempty + rt), (tile_i & 1) ^ 1, p.err, 5);       // previous tile's MMAs are done with A
-      float xx = 0.f;
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int j = jj;                         // chunk j of 8 consecutive dims (A stores are conflict-free)
-        float v[8];
+      const unsigned pp = tile_i & 1, u = tile_i >> 1;
+#pragma unroll 1
+      for (int rt = 0; rt < RT; ++rt) {
+        const long long n0 = tile * tile_rows + (long long)rt * R;
+        const int rows = (int)max(0LL, min((long long)R, p.z.N - n0));
+        unsigned char* buf = sBuf + (size_t)(rt * 2 + pp) * BUF_BYTES;
+        const float* raw = reinterpret_cast<const float*>(buf);
+        float v[D];
+        if (staged && rows > 0) mbar_wait(smem_u32(rawfull + rt * 2 + pp), u & 1, p.err, 8);
+        else mbar_wait(smem_u32(aempty + rt * 2 + pp), (u & 1) ^ 1, p.err, 5);     // nobody fills it for us: wait until free
         if (row < rows) {
+          const long long n = n0 + row;
           if (p.stage_mode == STG_ROWS) {
-            const float4 f0 = *reinterpret_cast<const float4*>(src + j * 8);
-            const float4 f1 = *reinterpret_cast<const float4*>(src + j * 8 + 4);
-            v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w; v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
+            const float4* src = reinterpret_cast<const float4*>(raw + row * D);
+#pragma unroll
+            for (int c = 0; c < D / 4; ++c) {
+              const float4 f = src[c];
+              v[4 * c] = f.x; v[4 * c + 1] = f.y; v[4 * c + 2] = f.z; v[4 * c + 3] = f.w;
+            }
           } else if (p.stage_mode == STG_BCT) {
+            const int T = (int)p.z.T;
+            const long long b = n / T; const int t = (int)(n - b * T);
+            const float* src = raw + (b - n0 / T) * (D * T) + t;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = src[(j * 8 + e) * sstride];
+            for (int k = 0; k < D; ++k) v[k] = src[k * T];
           } else {
+            const float* src = p.z.p + p.z.row_base(n);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __ldg(p.z.p + goff + (long long)(j * 8 + e) * p.z.sC);
+            for (int k = 0; k < D; ++k) v[k] = __ldg(src + (long long)k * p.z.sC);
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+          for (int k = 0; k < D; ++k) v[k] = 0.f;
         }
-        uint32_t hw[4], lw[4];
+        converter_sync();                          // every raw read of this buffer is done
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = v[j * 8 + 2 * e], b = v[j * 8 + 2 * e + 1];
+            hw[e] = pack_bf16x2(a, b);
+            lw[e] = pack_bf16x2(a - __uint_as_float(hw[e] << 16), b - __uint_as_float(hw[e] & 0xFFFF0000u));
+          }
+          const int off = row * 128 + ((j ^ (row & 7)) << 4);
+          *reinterpret_cast<uint4*>(buf + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(buf + A_HALF + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)
+        converter_sync();
+        if (lane == 0) mbar_arrive(smem_u32(afull + rt * 2 + pp));
+      }
+    }
+  } else {
+    // ================= epilogue groups (4 warps = 128 rows each) =================
+    const int rt = (warp - 2) >> 2;
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                // accumulator lane == row inside the row tile
+    const float emax = p.info[0];
+    const bool cb_bad = p.info[1] != 0.f;
+    const uint32_t mask = 0xFFFFFF80u;
+    unsigned it = 0, tile_i = 0;
+    for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_i) {
+      const unsigned pp = tile_i & 1, u = tile_i >> 1;
+      const long long n0 = tile * tile_rows + (long long)rt * R;
+      const int rows = (int)max(0LL, min((long long)R, p.z.N - n0));
+      // |x|^2 of this thread's row from the split operands (only feeds the error bound)
+      mbar_wait(smem_u32(afull + rt * 2 + pp), u & 1, p.err, 10);
+      const unsigned char* a_hi = sBuf + (size_t)(rt * 2 + pp) * BUF_BYTES;
+      float xx = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int off = row * 128 + ((j ^ (row & 7)) << 4);
+        const uint4 h = *reinterpret_cast<const uint4*>(a_hi + off);
+        const uint4 l = *reinterpret_cast<const uint4*>(a_hi + A_HALF + off);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float a = v[2 * e], b = v[2 * e + 1];
-          xx = fmaf(a, a, xx); xx = fmaf(b, b, xx);
-          hw[e] = pack_bf16x2(a, b);
-          lw[e] = pack_bf16x2(a - __uint_as_float(hw[e] << 16), b - __uint_as_float(hw[e] & 0xFFFF0000u));
+          const float v0 = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+          const float v1 = __uint_as_float(hw[e] & 0xFFFF0000u) + __uint_as_float(lw[e] & 0xFFFF0000u);
+          xx = fmaf(v0, v0, xx); xx = fmaf(v1, v1, xx);
         }
-        const int off = row * 128 + ((j ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       }
-      fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core (async proxy)
-      group_sync(1 + rt);
-      if (lane == 0) {
-        mbar_arrive(smem_u32(afull + rt));
-        if (use_stage) mbar_arrive(smem_u32(sempty + rt));   // staging may be refilled for the NEXT tile now
-      }
-      // ---- epilogue: running top-2 of s_k = x.E_k - |E_k|^2/2 over all code tiles ----
+      // ---- running top-2 of s_k = x.E_k - |E_k|^2/2 over all code tiles ----
       float g1 = -INFINITY, g2 = -INFINITY; int gi = 0;
       for (int j = 0; j < NT; ++j, ++it) {
         const unsigned as = it & 1;
         mbar_wait(smem_u32(tfull + as * RT + rt), (it >> 1) & 1, p.err, 6);
-        mbar_wait(smem_u32(full + it % NST), (it / NST) & 1, p.err, 9);    // acquire the bulk-copied -|E|^2/2 slot
+        mbar_wait(smem_u32(nhfull + it % NHS), (it / NHS) & 1, p.err, 9);  // acquire the bulk-copied -|E|^2/2 slot
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * RT + rt) * BN);
         const float4* nh = reinterpret_cast<const float4*>(sN + (size_t)(it % NHS) * BN);
@@ -359,6 +392,7 @@ vq_assign_tc_kernel(const Params p) {
           uint32_t (&nxt)[32] = (c & 1) ? va : vb;
           tmem_ld_wait();
           if (c + 1 < BN / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);     // overlaps with the math below
+          if (p.dbg & 1) { t1 = fmaxf(t1, __uint_as_float(cur[0] ^ cur[13] ^ cur[31])); continue; }
 #pragma unroll
           for (int e4 = 0; e4 < 8; ++e4) {
             const float4 h = nh[c * 8 + e4];
@@ -439,6 +473,7 @@ int launch_assign_tc(const ZView& z, const float* E, const float* ee, const void
   p.list = wsi + 64;
   p.list_count = wsi;
   p.err = wsi + 1;
+  { const char* d = getenv("VQB200_TC_DEBUG"); p.dbg = d ? atoi(d) : 0; }
   // how the raw fp32 rows reach shared memory: one bulk-TMA copy per 128-row tile when the rows of a
   // tile form one contiguous, 16-byte aligned byte range that fits the staging buffer
   p.stage_mode = STG_DIRECT;
