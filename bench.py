@@ -130,6 +130,12 @@ def cpu_reference_arm(cfg, steps, warmup, sample_windows=None):
         fw = rvq_forward(z, stages, True)
         rvq_backward(fw, stages, g, 1.0)
 
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host core
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=os.cpu_count())
+    except Exception:  # pragma: no cover
+        limiter = None
     for _ in range(max(1, min(warmup, 2))):
         step()
     times = []
@@ -137,6 +143,8 @@ def cpu_reference_arm(cfg, steps, warmup, sample_windows=None):
         t0 = time.perf_counter()
         step()
         times.append(time.perf_counter() - t0)
+    if limiter is not None:
+        limiter.restore_original_limits()
     times.sort()
     med = times[len(times) // 2]
     n = Bs * T

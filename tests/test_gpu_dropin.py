@@ -1,0 +1,112 @@
+"""Drop-in behaviour of `models/vqvae.py` on the GPU: a teacher-style training loop shaped like the reference's
+(scripts/train_ablation.py:195-229: AdamW 2e-4, loss = recon + loss_vq + 0.5*velocity term), checkpoint round trip
+(`:276-290`, `:357-364`), student-style double call of the shared quantizer, and B=1 eval windows like
+scripts/deployment/export_motion.py:51-71."""
+import io
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _teacher_steps(model, steps, batch, window, robot_dim):
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=2e-4, weight_decay=1e-4)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    base = torch.randn(batch, window, robot_dim, device=DEV, generator=g)
+    losses = []
+    model.train()
+    for _ in range(steps):
+        opt.zero_grad()
+        out = model(x_robot=base)
+        recon, loss_vq = out["robot"]["recon"], out["robot"]["loss_vq"]
+        if loss_vq.ndim > 0:
+            loss_vq = loss_vq.mean()
+        loss = F.mse_loss(recon, base) + loss_vq + 0.5 * F.mse_loss(recon[:, :, 1:] - recon[:, :, :-1],
+                                                                     base[:, :, 1:] - base[:, :, :-1])
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+        for k, v in out["robot"]["metrics"].items():
+            assert v.ndim == 0 and v.is_cuda, k
+    return losses
+
+
+@pytest.mark.parametrize("arch,method,batch", [("transformer", "hybrid", 512), ("resnet_no_down", "ema", 256),
+                                               ("resnet_no_down", "rvq", 64), ("resnet_no_down", "standard", 64),
+                                               ("simple", "fsq", 32), ("resnet", "lfq", 32), ("resnet_no_down", "ae", 16)])
+def test_teacher_training_runs_and_learns(arch, method, batch):
+    from models.vqvae import DualMotionVQVAE
+    torch.manual_seed(42)
+    window = 10 if arch in ("transformer", "resnet_no_down") else 16
+    model = DualMotionVQVAE(human_input_dim=126, robot_input_dim=29, hidden_dim=64, arch=arch, method=method,
+                            window_size=window).to(DEV)
+    losses = _teacher_steps(model, 12, batch, window, 29)
+    assert all(map(lambda v: v == v and abs(v) < 1e12, losses)), losses
+    if method in ("ae", "fsq", "standard"):
+        assert losses[-1] < losses[0]
+    # checkpoint round trip through the reference's two formats
+    buf = io.BytesIO()
+    torch.save({"epoch": 0, "model_state_dict": model.state_dict(), "config": {}}, buf)
+    buf.seek(0)
+    sd = torch.load(buf, map_location=DEV)["model_state_dict"]
+    clone = DualMotionVQVAE(human_input_dim=126, robot_input_dim=29, hidden_dim=64, arch=arch, method=method,
+                            window_size=window).to(DEV)
+    clone.load_state_dict({("module." + k)[7:]: v for k, v in sd.items()}, strict=True)
+    model.eval(); clone.eval()
+    x = torch.randn(1, window, 29, device=DEV)                      # export_motion.py: one window at a time
+    with torch.no_grad():
+        a = model(x_robot=x)["robot"]["recon"]
+        b = clone(x_robot=x)["robot"]["recon"]
+    assert torch.equal(a, b)
+
+
+def test_student_mode_double_call_updates_ema_twice():
+    """Both branches call the shared quantizer; with everything but human_encoder frozen the EMA buffers still
+    move (reference models/vqvae.py:43-50 ignores requires_grad)."""
+    from models.vqvae import DualMotionVQVAE
+    torch.manual_seed(0)
+    m = DualMotionVQVAE(human_input_dim=12, robot_input_dim=7, hidden_dim=64, codebook_size=64, arch="resnet_no_down",
+                        method="ema", window_size=10).to(DEV)
+    for n, p in m.named_parameters():
+        p.requires_grad = n.startswith("human_encoder")
+    m.train()
+    B = 32
+    out = m(x_robot=torch.randn(B, 10, 7, device=DEV), x_human=torch.randn(B, 10, 12, device=DEV))
+    n = B * 10
+    expect = 0.99 * (0.01 * n) + 0.01 * n
+    assert abs(float(m.quantizer.ema_cluster_size.sum()) - expect) / expect < 1e-5
+    loss = out["human"]["loss_vq"] + F.mse_loss(out["human"]["z_e"], out["robot"]["z_e"].detach())
+    loss.backward()
+    assert m.human_encoder.model[0].weight.grad is not None
+    assert m.quantizer.embedding.weight.grad is None
+
+
+def test_cuda_graph_capture_of_the_quantizer_step():
+    """No host sync anywhere in the path: forward + backward of the hybrid quantizer replays from a CUDA graph."""
+    import vqb200
+    torch.manual_seed(1)
+    q = vqb200.HybridVQ(64, [8, 5, 5, 5], vq_codebook_size=512).to(DEV).train()
+    z = torch.randn(512, 1, 64, device=DEV).permute(0, 2, 1).contiguous().permute(0, 2, 1).requires_grad_(True)
+    zs = torch.randn(512, 64, 1, device=DEV, requires_grad=True)
+    g = torch.randn(512, 64, 1, device=DEV)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):                                          # warm-up outside capture (allocations, attributes)
+            loss, out, met = q(zs)
+            torch.autograd.backward([out, loss], [g, torch.ones((), device=DEV)])
+            zs.grad = None
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    zs.grad = None
+    with torch.cuda.graph(graph):
+        loss, out, met = q(zs)
+        torch.autograd.backward([out, loss], [g, torch.ones((), device=DEV)])
+    cs0 = q.vq.layers[0].ema_cluster_size.clone()
+    graph.replay(); graph.replay()
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all() and torch.isfinite(zs.grad).all() and float(met["perplexity"]) > 0
+    assert not torch.equal(cs0, q.vq.layers[0].ema_cluster_size)      # EMA state advanced inside the replays
