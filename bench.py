@@ -406,6 +406,12 @@ def run_extras(torch, vqb200, dev, peaks):
         ms = timeit(s2, 30)
         res["cfg2_hybrid_n512"] = {"us_per_step": ms * 1e3, "vectors_per_s": 512 / (ms * 1e-3),
                                    "vqb200_launches_per_step": (vqb200._lib.launch_count() - l0) / 33}
+        gs = vqb200.GraphedQuantizerStep(hy, zz.detach())
+        ms = timeit(lambda: gs(zz.detach(), g2), 50)
+        res["cfg2_hybrid_n512_cuda_graph"] = {"us_per_step": ms * 1e3, "vectors_per_s": 512 / (ms * 1e-3)}
+        g1s = vqb200.GraphedQuantizerStep(mod, z.detach())
+        ms = timeit(lambda: g1s(z.detach(), g), 50)
+        res["cfg1_ema_k1024_n40960_cuda_graph"] = {"us_per_step": ms * 1e3, "vectors_per_s": cfg["B"] * cfg["T"] / (ms * 1e-3)}
         # cfg4: FSQ / LFQ elementwise stage, 1 048 576 windows x 10
         B = 1_048_576
         ze = 2.0 * torch.randn(B, 4, 10, device=dev)
