@@ -170,6 +170,154 @@ lfq_backward_kernel(const float* __restrict__ z_e, const float* __restrict__ g_z
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Tiled variants: a CTA streams a run of whole samples ([d,T] slabs, contiguous) through shared
+// memory with 16-byte accesses, quantises rows there (one (b,t) vector per thread, stride-T smem
+// reads) and streams the result back; indices are written as coalesced 8-byte stores.
+// ------------------------------------------------------------------------------------------
+constexpr int Q_TILE_ELEMS = 4096;
+constexpr int Q_NT = 256;
+constexpr long long Q_LOCAL_HALF = 1LL << 15;                 // CTA-local bitmap window [-2^15, 2^15)
+constexpr int Q_LOCAL_WORDS = (int)(2 * Q_LOCAL_HALF / 32);   // 2048 words = 8 KiB of shared memory
+
+template <bool IS_LFQ>
+__global__ void __launch_bounds__(Q_NT)
+fsq_lfq_tile_kernel(const float* __restrict__ z_e, long long B, int d, int T, int samples_per_tile,
+                    const int32_t* __restrict__ basis, double codebook_size, float weight,
+                    float* __restrict__ z_out, long long* __restrict__ idx, void* ws, float* __restrict__ outm) {
+  __shared__ __align__(16) float X[Q_TILE_ELEMS];
+  __shared__ unsigned lbm[Q_LOCAL_WORDS];        // codes this CTA has seen (window around 0): no global traffic per vector
+  const UniqWs w(ws);
+  const int tid = threadIdx.x;
+  const int slab = d * T;
+  for (int i = tid; i < Q_LOCAL_WORDS; i += Q_NT) lbm[i] = 0u;
+  float fb[FSQ_MAX_D];
+  if (!IS_LFQ) {
+#pragma unroll
+    for (int i = 0; i < FSQ_MAX_D; ++i) fb[i] = (i < d) ? (float)__ldg(basis + i) : 0.f;
+  }
+  const long long ntiles = (B + samples_per_tile - 1) / samples_per_tile;
+  float part = 0.f;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long b0 = tile * samples_per_tile;
+    const int ns = (int)min((long long)samples_per_tile, B - b0);
+    const int n = ns * slab;
+    const long long e0 = b0 * slab;
+    __syncthreads();
+    {
+      const float4* s4 = reinterpret_cast<const float4*>(z_e + e0);
+      float4* d4 = reinterpret_cast<float4*>(X);
+      for (int i = tid; i < (n >> 2); i += Q_NT) d4[i] = __ldg(s4 + i);
+      for (int i = (n & ~3) + tid; i < n; i += Q_NT) X[i] = __ldg(z_e + e0 + i);
+    }
+    __syncthreads();
+    const int rows = ns * T;
+    for (int r = tid; r < rows; r += Q_NT) {
+      const int bl = r / T, t = r - bl * T;
+      float* px = X + bl * slab + t;
+      long long code = 0;
+      if (IS_LFQ) {
+        for (int i = 0; i < d; ++i) {
+          const float z = px[i * T];
+          const float sgn = (z > 0.f) ? 1.f : -1.f;
+          const float zq = __fadd_rn(z, __fsub_rn(sgn, z));
+          px[i * T] = zq;
+          if (zq > 0.f) code |= (1LL << i);
+          // entropy term: only its mean enters the loss (1e-5 tolerance) -> MUFU-based fast intrinsics
+          const float p = __fdividef(1.f, 1.f + __expf(-z));
+          const float q = 1.f - p;
+          part -= fmaf(p, __logf(p + 1e-6f), q * __logf(q + 1e-6f));
+        }
+      } else {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < FSQ_MAX_D; ++i) {
+          if (i < d) {
+            const float z = px[i * T];
+            const float zh = __fadd_rn(z, __fsub_rn(rintf(z), z));
+            px[i * T] = zh;
+            const float p = __fmul_rn(zh, fb[i]);
+            s = (i == 0) ? p : __fadd_rn(s, p);
+          }
+        }
+        code = trunc_to_i64(s);
+      }
+      idx[b0 * T + r] = code;
+      if (code >= -Q_LOCAL_HALF && code < Q_LOCAL_HALF) {
+        const unsigned bit = (unsigned)(code + Q_LOCAL_HALF);
+        const unsigned m = 1u << (bit & 31);
+        if (!(lbm[bit >> 5] & m)) atomicOr(&lbm[bit >> 5], m);
+      } else {
+        unique_insert(w, code);                    // rare: global bitmap / hash set, counted there
+      }
+    }
+    __syncthreads();
+    {
+      const float4* s4 = reinterpret_cast<const float4*>(X);
+      float4* d4 = reinterpret_cast<float4*>(z_out + e0);
+      for (int i = tid; i < (n >> 2); i += Q_NT) d4[i] = s4[i];
+      for (int i = (n & ~3) + tid; i < n; i += Q_NT) z_out[e0 + i] = X[i];
+    }
+  }
+  // merge the CTA-local bitmap into the global one (its bits are counted by the last CTA, not incrementally)
+  __syncthreads();
+  {
+    unsigned* gbm = w.bitmap + (unsigned)((UNIQ_HALF - Q_LOCAL_HALF) >> 5);
+    for (int i = tid; i < Q_LOCAL_WORDS; i += Q_NT) { const unsigned v = lbm[i]; if (v) atomicOr(gbm + i, v); }
+  }
+  if (IS_LFQ) {
+    __shared__ double red[Q_NT / 32];
+    double p = warp_sum((double)part);
+    if ((tid & 31) == 0) red[tid >> 5] = p;
+    __syncthreads();
+    if (tid < 32) {
+      double v = tid < Q_NT / 32 ? red[tid] : 0.0;
+      v = warp_sum(v);
+      if (tid == 0) atomicAdd(w.ent, v);
+    }
+  }
+  __shared__ bool s_is_last;
+  __shared__ unsigned s_local_total;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) { s_is_last = (atomicAdd(w.ticket, 1u) == gridDim.x - 1); s_local_total = 0u; }
+  __syncthreads();
+  if (s_is_last) {
+    __threadfence();
+    const volatile unsigned* gbm = w.bitmap + (unsigned)((UNIQ_HALF - Q_LOCAL_HALF) >> 5);
+    unsigned c = 0;
+    for (int i = tid; i < Q_LOCAL_WORDS; i += Q_NT) c += __popc(gbm[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((tid & 31) == 0 && c) atomicAdd(&s_local_total, c);
+  }
+  __syncthreads();
+  if (s_is_last && tid == 0) {
+    const unsigned u = atomicAdd(w.count, 0u) + s_local_total;
+    const bool ovf = atomicAdd(w.overflow, 0u) != 0u;
+    if (IS_LFQ) {
+      const double sum = atomicAdd(w.ent, 0.0);
+      const float mean = (float)(sum / ((double)B * T * d));
+      outm[0] = __fmul_rn(-mean, weight);
+      outm[1] = ovf ? NAN : (float)u;
+      outm[2] = ovf ? NAN : (float)(1.0 - (double)u / exp2((double)d));
+    } else {
+      outm[0] = ovf ? NAN : (float)u;
+      outm[1] = ovf ? NAN : (float)(1.0 - (double)u / codebook_size);
+    }
+  }
+}
+
+// samples per tile for the tiled kernels (0 = not eligible)
+static int q_samples_per_tile(const void* a, const void* b, int64_t d, int64_t T) {
+  const long long slab = d * T;
+  if (slab <= 0 || slab > Q_TILE_ELEMS / 4) return 0;
+  if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15)) return 0;
+  long long s = (Q_TILE_ELEMS / slab) & ~3LL;          // multiple of 4 samples keeps every tile 16-byte aligned
+  return (int)s;
+}
+
 }  // namespace vqb200
 
 using namespace vqb200;
@@ -187,6 +335,13 @@ int vqb200_fsq_forward(const float* z_e, int64_t B, int64_t d, int64_t T, const 
   VQ_CHECK_ARG(codebook_size > 0, VQB200_EINVAL, "fsq_forward: codebook_size must be positive");
   VQ_CUDA(cudaMemsetAsync(workspace, 0, UNIQ_WS_BYTES, stream));
   const long long N = B * T;
+  if (const int spt = q_samples_per_tile(z_e, z_hard, d, T)) {
+    const int grid = (int)max(1LL, min((long long)((B + spt - 1) / spt), (long long)sm_count() * 8));
+    fsq_lfq_tile_kernel<false><<<grid, Q_NT, 0, stream>>>(z_e, B, (int)d, (int)T, spt, basis, (double)codebook_size, 0.f,
+                                                         z_hard, (long long*)idx, workspace, out2);
+    VQ_LAUNCH_CHECK("fsq_lfq_tile_kernel<FSQ>");
+    return VQB200_OK;
+  }
   const int grid = grid_for(N, 256, sm_count() * 8);
   fsq_forward_kernel<<<grid, 256, 0, stream>>>(z_e, B, (int)d, (int)T, basis, (double)codebook_size, z_hard,
                                                (long long*)idx, workspace, out2);
@@ -201,6 +356,13 @@ int vqb200_lfq_forward(const float* z_e, int64_t B, int64_t d, int64_t T, float 
   VQ_CHECK_ARG(B > 0 && T > 0 && d > 0 && d <= LFQ_MAX_D, VQB200_ESHAPE, "lfq_forward: unsupported shape d=%lld (max %d, B>0)", (long long)d, LFQ_MAX_D);
   VQ_CUDA(cudaMemsetAsync(workspace, 0, UNIQ_WS_BYTES, stream));
   const long long N = B * T;
+  if (const int spt = q_samples_per_tile(z_e, z_q, d, T)) {
+    const int grid = (int)max(1LL, min((long long)((B + spt - 1) / spt), (long long)sm_count() * 8));
+    fsq_lfq_tile_kernel<true><<<grid, Q_NT, 0, stream>>>(z_e, B, (int)d, (int)T, spt, nullptr, 0.0, entropy_loss_weight,
+                                                        z_q, (long long*)idx, workspace, out3);
+    VQ_LAUNCH_CHECK("fsq_lfq_tile_kernel<LFQ>");
+    return VQB200_OK;
+  }
   const int grid = grid_for(N, 256, sm_count() * 8);
   lfq_forward_kernel<<<grid, 256, 0, stream>>>(z_e, B, (int)d, (int)T, entropy_loss_weight, z_q, (long long*)idx,
                                                workspace, out3);
