@@ -29,6 +29,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "codebook.cuh"
+#include "ptx.cuh"
 
 namespace vqb200 {
 
@@ -53,38 +54,9 @@ constexpr int SMEM_BAR = 256;
 constexpr int SMEM_TOTAL = SMEM_BUF + SMEM_B + SMEM_NH + SMEM_BAR;   // 232192 <= 232448
 enum StageMode : int { STG_DIRECT = 0, STG_ROWS = 1, STG_BCT = 2 };
 constexpr int NTHREADS = 448;
-constexpr unsigned SPIN_LIMIT = 1u << 22;   // bounded waits: a protocol bug traps instead of hanging the GPU
 
-// ---- PTX wrappers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
-  unsigned spins = 0;
-  while (!mbar_try(bar, parity)) {
-    if (++spins > SPIN_LIMIT) { if (err) atomicExch(err, code); __trap(); }
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// ---- tcgen05 / TMEM PTX wrappers (mbarrier + bulk-TMA wrappers live in ptx.cuh) ---------------
+using namespace ptx;
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
@@ -270,9 +242,10 @@ vq_assign_tc_kernel(const Params p) {
             tc_fence_after();
             const uint32_t a_hi = smem_u32(sBuf + (size_t)(rt * 2 + pp) * BUF_BYTES), a_lo = a_hi + A_HALF;
             const uint32_t d_tmem = tmem_base + (uint32_t)((as * RT + rt) * BN);
-#pragma unroll
             const int nkb = (p.dbg & 2) ? 1 : 3;
-            for (int kb = 0; kb < nkb; ++kb) {          // x_hi.E_hi + x_lo.E_hi + x_hi.E_lo
+#pragma unroll
+            for (int kb = 0; kb < 3; ++kb) {            // x_hi.E_hi + x_lo.E_hi + x_hi.E_lo
+              if (kb >= nkb) break;
               const uint32_t a = (kb == 1) ? a_lo : a_hi;
               const uint32_t b = (kb == 2) ? b_lo : b_hi;
 #pragma unroll

@@ -8,7 +8,9 @@
 //   3. stream the results back.
 // Used by vq_gather_st (K2), vq_backward_input (K2b) and ema_accumulate (K3a); the generic strided
 // kernels in gather.cu / ema.cu remain the fallback for arbitrary views.
+#include <stdlib.h>
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace vqb200 {
 
@@ -102,7 +104,7 @@ gather_tile_kernel(const float* __restrict__ z, const float* __restrict__ E, con
         if (mode == GM_PLAIN) X[a] = st;
         else {
           X[a] = __fsub_rn(x, st);
-          Y[a] = __fadd_rn(need_y_in ? Y[a] : 0.f, st);
+          if (o2) Y[a] = __fadd_rn(need_y_in ? Y[a] : 0.f, st);
         }
       }
     }
@@ -110,6 +112,131 @@ gather_tile_kernel(const float* __restrict__ z, const float* __restrict__ E, con
     if (o1) tile_copy_out(o1 + e0, X, n, tid);
     if (mode == GM_RVQ && o2) tile_copy_out(o2 + e0, Y, n, tid);
   }
+  if (sse) {
+    __shared__ double red[TILE_NT / 32];
+    double p = warp_sum((double)part);
+    if ((tid & 31) == 0) red[tid >> 5] = p;
+    __syncthreads();
+    if (tid < 32) {
+      double v = tid < TILE_NT / 32 ? red[tid] : 0.0;
+      v = warp_sum(v);
+      if (tid == 0 && v != 0.0) atomicAdd(sse, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Bulk-TMA pipelined variant of gather_tile_kernel: tiles are prefetched STAGES-1 ahead with
+// cp.async.bulk (completion on mbarriers), transformed in place in shared memory and written back
+// with cp.async.bulk shared->global (bulk async-groups), so loads, math and stores of different
+// tiles overlap inside one CTA and the SM always has >= 2 tiles of reads in flight.
+// ------------------------------------------------------------------------------------------
+constexpr int BULK_STAGES = 3;
+
+template <bool TWO>      // TWO: second operand/result buffer Y (RVQ running sum, or upstream gradient)
+__global__ void __launch_bounds__(TILE_NT)
+gather_bulk_kernel(const float* __restrict__ z, const float* __restrict__ E, const int32_t* __restrict__ idx,
+                   int K, TileGeom g, int mode, float* __restrict__ o1, float* __restrict__ o2,
+                   const float* __restrict__ in2, int accum_init, const float* __restrict__ g_loss, float coef,
+                   double* __restrict__ sse) {
+  using namespace ptx;
+  extern __shared__ __align__(128) float smem[];
+  constexpr int STAGE_FLOATS = (TWO ? 2 : 1) * TILE_ELEMS;
+  __shared__ uint64_t full[BULK_STAGES];
+  __shared__ int s_off[256];
+  __shared__ int s_code[2][256];
+  const int tid = threadIdx.x;
+  const int D = g.D, T = g.T;
+  const float scale = (mode == GM_BACKWARD) ? __fmul_rn(g_loss ? __ldg(g_loss) : 1.0f, coef) : 0.f;
+  const bool y_in = TWO && ((mode == GM_RVQ && accum_init) || mode == GM_BACKWARD);
+  const float* ysrc = (mode == GM_BACKWARD) ? in2 : o2;
+  if (tid == 0) {
+    for (int s = 0; s < BULK_STAGES; ++s) mbar_init(smem_u32(full + s), 1);
+    fence_barrier_init();
+  }
+  if (tid < g.rows_per_tile) { const int b = tid / T, t = tid - b * T; s_off[tid] = b * D * T + t; }
+  __syncthreads();
+
+  const long long my_tiles = (g.ntiles > blockIdx.x) ? (g.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto tile_rows = [&](long long i) {
+    const long long r0 = (blockIdx.x + i * gridDim.x) * g.rows_per_tile;
+    return (int)min((long long)g.rows_per_tile, g.N - r0);
+  };
+  auto issue_load = [&](long long i) {           // thread 0 only
+    const int s = (int)(i % BULK_STAGES);
+    const long long r0 = (blockIdx.x + i * gridDim.x) * g.rows_per_tile;
+    const uint32_t bytes = (uint32_t)tile_rows(i) * D * 4;
+    float* X = smem + (size_t)s * STAGE_FLOATS;
+    mbar_expect_tx(smem_u32(full + s), y_in ? 2 * bytes : bytes);
+    bulk_g2s(smem_u32(X), z + r0 * D, bytes, smem_u32(full + s));
+    if (y_in) bulk_g2s(smem_u32(X + TILE_ELEMS), ysrc + r0 * D, bytes, smem_u32(full + s));
+  };
+  if (tid == 0) for (long long i = 0; i < my_tiles && i < BULK_STAGES - 1; ++i) issue_load(i);
+  if (my_tiles > 0 && tid < tile_rows(0)) {
+    const int k = __ldg(idx + (long long)blockIdx.x * g.rows_per_tile + tid);
+    s_code[0][tid] = min(max(k, 0), K - 1);
+  }
+  float part = 0.f;
+  for (long long i = 0; i < my_tiles; ++i) {
+    const int s = (int)(i % BULK_STAGES);
+    const long long r0 = (blockIdx.x + i * gridDim.x) * g.rows_per_tile;
+    const int rows = tile_rows(i);
+    const int n = rows * D;
+    float* X = smem + (size_t)s * STAGE_FLOATS;
+    float* Y = X + TILE_ELEMS;
+    // prefetch the codes of the next tile into registers (stored after the math)
+    int next_code = 0;
+    const bool have_next = (i + 1 < my_tiles) && tid < tile_rows(i + 1);
+    if (have_next) next_code = __ldg(idx + (blockIdx.x + (i + 1) * gridDim.x) * (long long)g.rows_per_tile + tid);
+    if (tid == 0 && i + BULK_STAGES - 1 < my_tiles) {
+      bulk_wait_read<0>();                       // the store that last read stage (i-1)%STAGES has drained it
+      issue_load(i + BULK_STAGES - 1);
+    }
+    __syncthreads();                             // s_code[i&1] written (previous iteration / prologue)
+    mbar_wait(smem_u32(full + s), (uint32_t)((i / BULK_STAGES) & 1), nullptr, 0);
+    const int* code = s_code[i & 1];
+    constexpr int U = 8;                         // codeword gathers in flight per thread (L2 latency hiding)
+    for (int e0 = tid; e0 < n; e0 += TILE_NT * U) {
+      int a[U]; float q[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * TILE_NT;
+        if (e < n) {
+          const int r = g.dshift >= 0 ? (e >> g.dshift) : (e / D);
+          const int k = e - r * D;
+          a[u] = s_off[r] + k * T;
+          q[u] = __ldg(E + (size_t)code[r] * D + k);
+        } else { a[u] = -1; q[u] = 0.f; }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (a[u] < 0) continue;
+        const float x = X[a[u]];
+        if (mode == GM_BACKWARD) {
+          X[a[u]] = fmaf(scale, __fsub_rn(x, q[u]), y_in ? Y[a[u]] : 0.f);
+        } else {
+          const float diff = __fsub_rn(q[u], x);
+          const float st = __fadd_rn(x, diff);
+          part = fmaf(diff, diff, part);
+          if (mode == GM_PLAIN) X[a[u]] = st;
+          else {
+            X[a[u]] = __fsub_rn(x, st);
+            if (TWO) Y[a[u]] = __fadd_rn(y_in ? Y[a[u]] : 0.f, st);
+          }
+        }
+      }
+    }
+    if (have_next) s_code[(i + 1) & 1][tid] = min(max(next_code, 0), K - 1);
+    fence_proxy_async();                         // generic-proxy smem writes -> visible to the bulk store
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)n * 4;
+      if (o1) bulk_s2g(o1 + r0 * D, smem_u32(X), bytes);
+      if (TWO && mode == GM_RVQ && o2) bulk_s2g(o2 + r0 * D, smem_u32(Y), bytes);
+      bulk_commit();
+    }
+  }
+  if (tid == 0) bulk_wait_all<0>();
   if (sse) {
     __shared__ double red[TILE_NT / 32];
     double p = warp_sum((double)part);
@@ -180,7 +307,27 @@ int try_gather_tile(const ZView& z, const float* E, const int32_t* idx, int K, i
   if (!tile_geom(z, g)) return 0;
   if ((reinterpret_cast<uintptr_t>(o1) & 15) || (reinterpret_cast<uintptr_t>(o2) & 15) ||
       (reinterpret_cast<uintptr_t>(in2) & 15) || (reinterpret_cast<uintptr_t>(E) & 3)) return 0;
-  const bool two = (mode == GM_RVQ) || (mode == GM_BACKWARD && in2);
+  const bool two = (mode == GM_RVQ && o2) || (mode == GM_BACKWARD && in2);
+  static const bool use_bulk = !(getenv("VQB200_NO_BULK") && atoi(getenv("VQB200_NO_BULK")));
+  if (use_bulk && (g.rows_per_tile * g.D * 4) % 16 == 0) {
+    const size_t smem = (size_t)BULK_STAGES * (two ? 2 : 1) * TILE_ELEMS * sizeof(float);
+    static thread_local bool configured = false;
+    if (!configured) {
+      cudaError_t e1 = cudaFuncSetAttribute(gather_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            BULK_STAGES * 2 * TILE_ELEMS * (int)sizeof(float));
+      cudaError_t e2 = cudaFuncSetAttribute(gather_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            BULK_STAGES * TILE_ELEMS * (int)sizeof(float));
+      if (e1 != cudaSuccess || e2 != cudaSuccess) return cuda_fail(e1 != cudaSuccess ? e1 : e2, "cudaFuncSetAttribute(gather_bulk_kernel)");
+      configured = true;
+    }
+    const int grid = tile_grid(g, two ? 2 : 4);
+    if (two) gather_bulk_kernel<true><<<grid, TILE_NT, smem, stream>>>(z.p, E, idx, K, g, mode, o1, o2, in2, accum_init, g_loss, coef, sse);
+    else gather_bulk_kernel<false><<<grid, TILE_NT, smem, stream>>>(z.p, E, idx, K, g, mode, o1, o2, in2, accum_init, g_loss, coef, sse);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "gather_bulk_kernel");
+    return 1;
+  }
   const size_t smem = (two ? 2 : 1) * TILE_ELEMS * sizeof(float);
   gather_tile_kernel<<<tile_grid(g, 8), TILE_NT, smem, stream>>>(z.p, E, idx, K, g, mode, o1, o2, in2, accum_init,
                                                                 g_loss, coef, sse);
