@@ -23,7 +23,7 @@ _SIGNATURES = {
     "vqb200_launch_count": (c_int64, []),
     "vqb200_codebook_image_bytes": (c_size_t, [c_int64, c_int64]),
     "vqb200_codebook_prepare": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P]),
-    "vqb200_assign_workspace_bytes": (c_size_t, [c_int64]),
+    "vqb200_assign_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "vqb200_vq_assign": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                  _P, _P, _P, _P, c_int64, _P, _P, _P, c_size_t, c_int, _P]),
     "vqb200_ema_accumulate": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,

@@ -12,13 +12,21 @@ int launch_assign_tc(const ZView& z, const float* E, const float* ee, const void
                      int K, int D, int32_t* idx, float* best, void* workspace, size_t workspace_bytes,
                      cudaStream_t stream);
 size_t assign_tc_workspace_bytes(long long N);
+bool assign_tc_gen_eligible(const ZView& z, int K, int D);
+int launch_assign_tc_gen(const ZView& z, const float* E, const float* ee, const void* image, const float* info,
+                         int K, int D, int32_t* idx, float* best, void* workspace, size_t workspace_bytes,
+                         cudaStream_t stream);
+size_t assign_tc_gen_workspace_bytes(long long N, int D);
 }  // namespace vqb200
 
 using namespace vqb200;
 
 extern "C" {
 
-size_t vqb200_assign_workspace_bytes(int64_t N) { return assign_tc_workspace_bytes(N); }
+size_t vqb200_assign_workspace_bytes(int64_t N, int64_t D) {
+  if (D == 128 || D == 256) return assign_tc_gen_workspace_bytes(N, (int)D);
+  return assign_tc_workspace_bytes(N);
+}
 
 int vqb200_vq_assign(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,
                      const float* E, const float* ee, const void* image, const float* info, int64_t K,
@@ -33,17 +41,20 @@ int vqb200_vq_assign(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB
   const ZView zv = make_zview(z, B, C, T, sB, sC, sT);
   const int D = (int)C;
   bool use_tc = false;
+  const bool gen = assign_tc_gen_eligible(zv, (int)K, D);          // D = 128 / 256: bf16 row-image variant
+  const bool eligible = gen || assign_tc_eligible(zv, (int)K, D);  // D = 64: in-place conversion variant
+  const size_t need = vqb200_assign_workspace_bytes(zv.N, D);
   if (algo == VQB200_ASSIGN_TC) {
     VQ_CHECK_ARG(image && info && workspace, VQB200_EINVAL, "vq_assign(TC): image, info and workspace are required");
     VQ_CHECK_ARG(!best, VQB200_EUNSUPPORTED, "vq_assign(TC): the winning distance is only produced by the SIMT algorithm");
-    VQ_CHECK_ARG(assign_tc_eligible(zv, (int)K, D), VQB200_EUNSUPPORTED, "vq_assign(TC): shape K=%lld D=%d not eligible", (long long)K, D);
+    VQ_CHECK_ARG(eligible, VQB200_EUNSUPPORTED, "vq_assign(TC): shape K=%lld D=%d not eligible (D must be 64, 128 or 256)", (long long)K, D);
     use_tc = true;
   } else if (algo == VQB200_ASSIGN_AUTO) {
-    use_tc = image && info && workspace && !best && assign_tc_eligible(zv, (int)K, D) &&
-             workspace_bytes >= assign_tc_workspace_bytes(zv.N) && zv.N >= 2048;
+    use_tc = image && info && workspace && !best && eligible && workspace_bytes >= need && zv.N >= 2048;
   } else {
     VQ_CHECK_ARG(algo == VQB200_ASSIGN_SIMT, VQB200_EINVAL, "vq_assign: unknown algo %d", algo);
   }
+  if (use_tc && gen) return launch_assign_tc_gen(zv, E, ee, image, info, (int)K, D, idx, best, workspace, workspace_bytes, stream);
   if (use_tc) return launch_assign_tc(zv, E, ee, image, info, (int)K, D, idx, best, workspace, workspace_bytes, stream);
   return launch_assign_simt(zv, E, ee, (int)K, D, idx, best, nullptr, nullptr, zv.N, stream);
 }

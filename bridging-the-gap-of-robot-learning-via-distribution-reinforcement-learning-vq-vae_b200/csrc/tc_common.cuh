@@ -1,0 +1,103 @@
+// vqb200 -- tcgen05 / TMEM wrappers and UMMA descriptors shared by the tensor-core assignment kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include "ptx.cuh"
+
+namespace vqb200 {
+namespace tcc {
+using namespace ptx;
+
+constexpr int TILE_M = 128;                 // rows per MMA (accumulator lanes)
+constexpr int BN = 128;                     // codes per accumulator (== IMG_TILE_CODES)
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+               " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+               :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                 "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 128-byte rows, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address        [0,14)
+  d |= (uint64_t)1 << 16;                           // leading byte offset  [16,30)  (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset   [32,46)
+  d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {      // a -> low half, b -> high half
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// (score & ~127) | column in ONE alu op: lop3 with LUT (a & c) | b
+__device__ __forceinline__ float pack_col(float s, uint32_t col, uint32_t mask) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEC;" : "=r"(r) : "r"(__float_as_uint(s)), "r"(col), "r"(mask));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// Running top-2 of one 32-column chunk of scores: s = acc + nh (nh = -|E|^2/2), column index packed into the low
+// 7 mantissa bits, 3.5 ALU ops per score.  `base` = first column of the chunk inside the 128-code tile.
+__device__ __forceinline__ void top2_chunk(const uint32_t (&cur)[32], const float4* nh, int base, uint32_t mask,
+                                           float& t1, float& t2) {
+#pragma unroll
+  for (int e4 = 0; e4 < 8; ++e4) {
+    const float4 h = nh[e4];
+    const int col = base + e4 * 4;
+    const float p0 = pack_col(__uint_as_float(cur[e4 * 4 + 0]) + h.x, col + 0, mask);
+    const float p1 = pack_col(__uint_as_float(cur[e4 * 4 + 1]) + h.y, col + 1, mask);
+    const float p2 = pack_col(__uint_as_float(cur[e4 * 4 + 2]) + h.z, col + 2, mask);
+    const float p3 = pack_col(__uint_as_float(cur[e4 * 4 + 3]) + h.w, col + 3, mask);
+    const float hi0 = fmaxf(p0, p1), lo0 = fminf(p0, p1);
+    t2 = fmax3(t2, lo0, fminf(t1, hi0));
+    t1 = fmaxf(t1, hi0);
+    const float hi1 = fmaxf(p2, p3), lo1 = fminf(p2, p3);
+    t2 = fmax3(t2, lo1, fminf(t1, hi1));
+    t1 = fmaxf(t1, hi1);
+  }
+}
+
+// Rigorous bound on the error of one score for a D-dim dot product done as 3 split-bf16 MMAs:
+// split remainder (3*2^-18) + fp32 accumulation over 3*D products (truncation assumed) + rounding of the
+// -|E|^2/2 add + 7 index bits packed into the mantissa.  mag = |x| * max|E|.
+__device__ __forceinline__ float score_error_bound(float mag, float emax, int D) {
+  const float acc = 3.0f * (float)D * 1.2e-7f;
+  return (1.15e-5f + acc + 1.6e-5f) * mag + 1.7e-5f * (0.5f * emax * emax);
+}
+
+}  // namespace tcc
+}  // namespace vqb200

@@ -49,7 +49,7 @@ class QuantizerState:
         return self.stats[self.K * self.D:]
 
     def assign_workspace(self, N: int) -> torch.Tensor:
-        need = int(_lib.load().vqb200_assign_workspace_bytes(N))
+        need = int(_lib.load().vqb200_assign_workspace_bytes(N, self.D))
         if self._assign_ws is None or self._assign_ws.numel() < need:
             self._assign_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._assign_ws

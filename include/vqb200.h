@@ -63,9 +63,10 @@ int vqb200_codebook_prepare(const float* E, int64_t K, int64_t D,
 /* ---- K1: fused distance + argmin ------------------- models/vqvae.py:30-38 (rows a2-a4) ----
  * idx[n] = first index of min_k fl(fl(|x_n|^2 + |E_k|^2) - 2 x_n.E_k); NaN distance wins.
  * Never materialises the N x K matrix.  idx: int32 [B*T].  best (optional, may be NULL): the
- * winning fp32 distance per row.  workspace: vqb200_assign_workspace_bytes(N) bytes
- * (may be NULL for the SIMT algorithm). */
-size_t vqb200_assign_workspace_bytes(int64_t N);
+ * winning fp32 distance per row (SIMT algorithm only).  workspace: vqb200_assign_workspace_bytes(N, D)
+ * bytes (may be NULL for the SIMT algorithm).  The tcgen05 path covers D = 64 (raw rows converted in shared
+ * memory) and D = 128 / 256 (input first split into a bf16 row image inside the workspace). */
+size_t vqb200_assign_workspace_bytes(int64_t N, int64_t D);
 int vqb200_vq_assign(const float* z, int64_t B, int64_t C, int64_t T,
                      int64_t sB, int64_t sC, int64_t sT,
                      const float* E, const float* ee, const void* image, const float* info,

@@ -39,7 +39,8 @@ def test_size_queries_need_no_gpu():
     assert lib.vqb200_codebook_image_bytes(1024, 64) == 8 * 32768 + 1024 * 4
     assert lib.vqb200_codebook_image_bytes(1000, 24) == 8 * 32768 + 1024 * 4
     assert lib.vqb200_unique_workspace_bytes() > 256 * 1024
-    assert lib.vqb200_assign_workspace_bytes(1000) >= 1000 * 4
+    assert lib.vqb200_assign_workspace_bytes(1000, 64) >= 1000 * 4
+    assert lib.vqb200_assign_workspace_bytes(1000, 256) >= 1024 * 256 * 4   # + split-bf16 row image
 
 
 def test_argument_errors_do_not_need_a_gpu():

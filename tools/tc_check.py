@@ -21,8 +21,7 @@ def timeit(fn, reps=5, warm=2):
     return a.elapsed_time(b) / reps
 
 
-def case(B, T, K, regime="small", seed=0, time_it=False, perm=False):
-    D = 64
+def case(B, T, K, regime="small", seed=0, time_it=False, perm=False, D=64):
     torch.manual_seed(seed)
     W = torch.randn(K, D, device=dev)
     if regime == "small":
@@ -41,10 +40,11 @@ def case(B, T, K, regime="small", seed=0, time_it=False, perm=False):
     i_simt = vqb200.vq_assign(z, W, st, _lib.ASSIGN_SIMT)
     i_tc = vqb200.vq_assign(z, W, st, _lib.ASSIGN_TC)
     torch.cuda.synchronize()
-    ws = st._assign_ws.view(torch.int32)
+    off = (-st._assign_ws.data_ptr()) % 1024 if D != 64 else 0
+    ws = st._assign_ws[off:off + 256].view(torch.int32)
     flagged, err = int(ws[0]), int(ws[1])
     mism = int((i_simt != i_tc).sum())
-    out = dict(B=B, T=T, K=K, regime=regime, perm=perm, N=B * T, mismatches=mism, flagged=flagged, err=err)
+    out = dict(B=B, T=T, K=K, D=D, regime=regime, perm=perm, N=B * T, mismatches=mism, flagged=flagged, err=err)
     if mism:
         bad = (i_simt != i_tc).reshape(-1).nonzero().reshape(-1)[:5]
         out["first_bad_rows"] = bad.tolist()
@@ -72,4 +72,11 @@ if __name__ == "__main__":
     total += case(100000, 10, 1024, time_it=True)
     total += case(1000000, 10, 1024, time_it=True)
     total += case(1000000, 1, 4096, "normal", time_it=True, perm=True)
+    total += case(300, 10, 256, D=128)
+    total += case(4096, 10, 1024, "normal", D=128, time_it=True)
+    total += case(1000, 1, 512, D=256, perm=True)
+    total += case(3686, 10, 1024, "degenerate", D=256)
+    total += case(1000000, 1, 4096, "normal", D=128, time_it=True, perm=True)
+    total += case(500000, 1, 4096, "normal", D=256, time_it=True, perm=True)
+    total += case(100000, 10, 2048, "small", D=256, time_it=True)
     print("TOTAL MISMATCHES", total)
