@@ -23,13 +23,12 @@ int launch_assign_simt(const ZView& z, const float* E, const float* ee, int K, i
 namespace tcg {
 using namespace tcc;
 
-constexpr int NST = 3;
-constexpr int NHS = 5;
-constexpr int NTHREADS = 192;
+constexpr int NHS = 5;                               // -|E|^2/2 ring (reuse distance >= ceil(NST/KB) + 2 code tiles)
+constexpr int NTHREADS = 320;                        // producer, MMA, 8 epilogue warps
 constexpr int A_BLOCK = 2 * TILE_M * 128;            // 32768: [x_hi | x_lo] for one 64-dim block
-constexpr int SMEM_B = NST * IMG_TILE_BYTES;
 constexpr int SMEM_NH = NHS * BN * 4;
 constexpr int SMEM_BAR = 256;
+constexpr int SMEM_XCH = TILE_M * 16;                // per-row (g1, g2, gi) hand-over between the two column halves
 
 // ---- z -> split-bf16 row image -------------------------------------------------------------------------
 // image tile (row tile rt, dim block kb) at byte offset (rt*KB + kb) * 32768: 16 KiB hi then 16 KiB lo,
@@ -78,9 +77,10 @@ struct Params {
   int* err;
 };
 
-template <int KB>
+template <int KB, int NST, bool EPI8>
 __global__ void __launch_bounds__(NTHREADS, 1)
 vq_assign_tc_gen_kernel(const Params p) {
+  constexpr int SMEM_B = NST * IMG_TILE_BYTES;
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int SMEM_A = KB * A_BLOCK;
   unsigned char* sA = smem;                       // [KB][hi 16K | lo 16K]
@@ -95,12 +95,13 @@ vq_assign_tc_gen_kernel(const Params p) {
   uint64_t* aempty = afull + 1;          // [1]
   uint64_t* nhfull = aempty + 1;         // [NHS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(nhfull + NHS);
+  float4* sX = reinterpret_cast<float4*>(sB + SMEM_B + SMEM_NH + SMEM_BAR);     // [128] top-2 exchange
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
     for (int s = 0; s < NHS; ++s) mbar_init(smem_u32(nhfull + s), 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), EPI8 ? 8 : 4); }
     mbar_init(smem_u32(afull), 1); mbar_init(smem_u32(aempty), 1);
     fence_barrier_init();
   }
@@ -165,8 +166,11 @@ vq_assign_tc_gen_kernel(const Params p) {
         }
       }
     }
-  } else {
+  } else if (EPI8 || warp < 6) {
+    // EPI8: two warps per TMEM lane quarter -- warp pair (w, w+4) shares rows and splits the 128 columns of a
+    // code tile; otherwise one warp per quarter scans all 128 columns
     const int q = warp & 3;
+    const int half = EPI8 ? ((warp - 2) >> 2) : 0;
     const int row = q * 32 + lane;
     const float emax = p.info[0];
     const bool cb_bad = p.info[1] != 0.f;
@@ -199,18 +203,23 @@ vq_assign_tc_gen_kernel(const Params p) {
         mbar_wait(smem_u32(tfull + as), (nt >> 1) & 1, p.err, 6);
         mbar_wait(smem_u32(nhfull + nt % NHS), (nt / NHS) & 1, p.err, 9);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-        const float4* nh = reinterpret_cast<const float4*>(sN + (size_t)(nt % NHS) * BN);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * 64;
+        const float4* nh = reinterpret_cast<const float4*>(sN + (size_t)(nt % NHS) * BN + half * 64);
         float t1 = -INFINITY, t2 = -INFINITY;
         uint32_t va[32], vb[32];
         tmem_ld32(taddr, va);
-#pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t (&cur)[32] = (c & 1) ? vb : va;
-          uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+        tmem_ld_wait();
+        tmem_ld32(taddr + 32, vb);
+        top2_chunk(va, nh, half * 64, mask, t1, t2);
+        tmem_ld_wait();
+        if (!EPI8) tmem_ld32(taddr + 64, va);
+        top2_chunk(vb, nh + 8, half * 64 + 32, mask, t1, t2);
+        if (!EPI8) {
           tmem_ld_wait();
-          if (c + 1 < BN / 32) tmem_ld32(taddr + (c + 1) * 32, nxt);
-          top2_chunk(cur, nh + c * 8, c * 32, mask, t1, t2);
+          tmem_ld32(taddr + 96, vb);
+          top2_chunk(va, nh + 16, 64, mask, t1, t2);
+          tmem_ld_wait();
+          top2_chunk(vb, nh + 24, 96, mask, t1, t2);
         }
         tc_fence_before();
         __syncwarp();
@@ -219,7 +228,18 @@ vq_assign_tc_gen_kernel(const Params p) {
         if (t1 > g1) { g2 = fmaxf(g1, t2); g1 = t1; gi = ti; }
         else { g2 = fmaxf(g2, t1); }
       }
-      if (row < rows) {
+      // merge the two column halves of every row (half 1 hands its top-2 to half 0)
+      if (EPI8) {
+        if (half == 1) sX[row] = make_float4(g1, g2, __int_as_float(gi), 0.f);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (half == 0) {
+          const float4 o = sX[row];
+          if (o.x > g1) { g2 = fmaxf(g1, o.y); g1 = o.x; gi = __float_as_int(o.z); }
+          else { g2 = fmaxf(g2, o.x); }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");        // sX free for the next tile
+      }
+      if (half == 0 && row < rows) {
         const long long n = n0 + row;
         const float mag = sqrtf(xx) * 1.0001f * emax;
         const float thr = 2.5f * score_error_bound(mag, emax, p.D);
@@ -237,17 +257,17 @@ vq_assign_tc_gen_kernel(const Params p) {
   if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
-template <int KB>
+template <int KB, int NST, bool EPI8>
 static int launch_kb(const Params& p, cudaStream_t stream) {
-  constexpr int smem = KB * A_BLOCK + SMEM_B + SMEM_NH + SMEM_BAR;
+  constexpr int smem = KB * A_BLOCK + NST * IMG_TILE_BYTES + SMEM_NH + SMEM_BAR + (EPI8 ? SMEM_XCH : 0);
   static_assert(smem <= 232448, "shared memory budget");
   static thread_local bool configured = false;
   if (!configured) {
-    VQ_CUDA(cudaFuncSetAttribute(vq_assign_tc_gen_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VQ_CUDA(cudaFuncSetAttribute(vq_assign_tc_gen_kernel<KB, NST, EPI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const int grid = (int)max(1LL, min(p.ntiles, (long long)sm_count()));
-  vq_assign_tc_gen_kernel<KB><<<grid, NTHREADS, smem, stream>>>(p);
+  vq_assign_tc_gen_kernel<KB, NST, EPI8><<<grid, NTHREADS, smem, stream>>>(p);
   VQ_LAUNCH_CHECK("vq_assign_tc_gen_kernel");
   return VQB200_OK;
 }
@@ -302,7 +322,7 @@ int launch_assign_tc_gen(const ZView& z, const float* E, const float* ee, const 
     VQ_LAUNCH_CHECK("z_image_kernel");
   }
   // 2. tcgen05 filter
-  int rc = (KB == 2) ? launch_kb<2>(p, stream) : launch_kb<4>(p, stream);
+  int rc = (KB == 2) ? launch_kb<2, 4, true>(p, stream) : launch_kb<4, 3, false>(p, stream);   // ring depth = what 227 KiB allows
   if (rc != VQB200_OK) return rc;
   // 3. exact re-do of the rows the filter could not prove
   return launch_assign_simt(z, E, ee, K, D, idx, best, p.list, p.list_count, z.N, stream);

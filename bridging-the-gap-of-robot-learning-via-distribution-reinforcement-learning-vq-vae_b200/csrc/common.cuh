@@ -76,21 +76,21 @@ __device__ __forceinline__ void load_rows(const ZView& z, long long n0, int rows
       }
     }
   } else if (z.mode == Z_BCT) {
-    const long long T = z.T;
-    const long long slab = (long long)D * T;
-    const long long b_lo = n0 / T;
-    const long long b_hi = (n0 + rows - 1) / T;
-    const long long total = (b_hi - b_lo + 1) * slab;
-    const float* base = z.p + b_lo * slab;
-    const long long row0 = b_lo * T;            // row id of (b_lo, t=0)
-    for (long long i = tid; i < total; i += nthreads) {
-      long long bl = i / slab;
-      int rem = (int)(i - bl * slab);
-      int k = rem / (int)T;
-      int t = rem - k * (int)T;
-      long long n = row0 + bl * T + t;
-      int r = (int)(n - n0);
-      if (r >= 0 && r < rows) st(r, k, __ldg(base + i));
+    // memory order of the C*T slabs the tile touches; 32-bit index math (a tile spans < 2^31 elements)
+    const unsigned T = (unsigned)z.T;
+    const unsigned slab = (unsigned)D * T;
+    const long long b_lo = n0 / z.T;
+    const long long b_hi = (n0 + rows - 1) / z.T;
+    const unsigned total = (unsigned)(b_hi - b_lo + 1) * slab;
+    const float* base = z.p + b_lo * (long long)slab;
+    const int row0 = (int)(b_lo * z.T - n0);    // row id (relative to the tile) of (b_lo, t=0); <= 0
+    for (unsigned i = tid; i < total; i += nthreads) {
+      const unsigned bl = i / slab;
+      const unsigned rem = i - bl * slab;
+      const unsigned k = rem / T;
+      const unsigned t = rem - k * T;
+      const int r = row0 + (int)(bl * T + t);
+      if (r >= 0 && r < rows) st(r, (int)k, __ldg(base + i));
     }
   } else {
     for (int i = tid; i < rows * D; i += nthreads) {
