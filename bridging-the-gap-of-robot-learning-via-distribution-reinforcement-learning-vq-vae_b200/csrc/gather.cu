@@ -9,6 +9,9 @@ int try_gather_tile(const ZView& z, const float* E, const int32_t* idx, int K, i
                     const float* in2, int accum_init, const float* g_loss, float coef, double* sse,
                     cudaStream_t stream);
 
+int try_rvq_chain(const ZView& z, int S, const float* const* E, const int32_t* const* idx, const int* K,
+                  double* const* sse, float* out, cudaStream_t stream);
+
 struct Decomp { long long b; int c, t; };
 
 __device__ __forceinline__ Decomp decomp(long long i, int C, int T, long long CT) {
@@ -130,6 +133,39 @@ int vqb200_vq_gather_st(const float* z, int64_t B, int64_t C, int64_t T, int64_t
   gather_st_kernel<<<grid_for(total, 256 * 4, sm_count() * 8), 256, 0, stream>>>(zv, E, idx, (int)K, out, residual,
                                                                                accum, accum_init, sse);
   VQ_LAUNCH_CHECK("gather_st_kernel");
+  return VQB200_OK;
+}
+
+int vqb200_rvq_output_chain(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,
+                             int32_t S, const float* const* E, const int32_t* const* idx, const int64_t* K,
+                             float* out, double* sse, float* scratch, vqb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VQ_CHECK_ARG(S >= 1 && S <= 8 && E && idx && K && out && sse, VQB200_EINVAL, "rvq_output_chain: bad arguments");
+  VQ_CHECK_ARG(B >= 0 && C > 0 && T > 0 && C * T < (1LL << 31), VQB200_ESHAPE, "rvq_output_chain: bad shape");
+  VQ_CUDA(cudaMemsetAsync(sse, 0, sizeof(double) * S, stream));
+  if (B * C * T == 0) return VQB200_OK;
+  const ZView zv = make_zview(z, B, C, T, sB, sC, sT);
+  int Ki[8]; double* ssep[8];
+  for (int s = 0; s < S; ++s) {
+    VQ_CHECK_ARG(E[s] && idx[s] && K[s] > 0, VQB200_EINVAL, "rvq_output_chain: null stage %d", s);
+    Ki[s] = (int)K[s]; ssep[s] = sse + s;
+  }
+  {
+    const int rc = try_rvq_chain(zv, S, E, idx, Ki, ssep, out, stream);
+    if (rc != 0) return rc == 1 ? VQB200_OK : rc;
+  }
+  // arbitrary views: replay the chain stage by stage with the generic strided kernel
+  // (scratch: B*C*T floats for the running residual; required on this path)
+  VQ_CHECK_ARG(S == 1 || scratch, VQB200_EWORKSPACE, "rvq_output_chain: scratch (B*C*T floats) needed for this layout");
+  const long long total = B * C * T;
+  const int grid = grid_for(total, 256 * 4, sm_count() * 8);
+  for (int s = 0; s < S; ++s) {
+    const bool first = s == 0, last = s == S - 1;
+    const ZView in = first ? zv : make_zview(scratch, B, C, T, C * T, T, 1);
+    gather_st_kernel<<<grid, 256, 0, stream>>>(in, E[s], idx[s], Ki[s], S == 1 ? out : nullptr, last ? nullptr : scratch,
+                                               S == 1 ? nullptr : out, first ? 0 : 1, sse + s);
+    VQ_LAUNCH_CHECK("gather_st_kernel(chain)");
+  }
   return VQB200_OK;
 }
 

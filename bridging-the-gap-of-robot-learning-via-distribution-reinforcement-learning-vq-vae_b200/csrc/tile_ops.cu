@@ -250,6 +250,139 @@ gather_bulk_kernel(const float* __restrict__ z, const float* __restrict__ E, con
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// RVQ output chain (models/vqvae.py:94-98 replayed for all stages at once).  Every stage's codebook is
+// updated exactly once per step, so after the last stage the whole value chain
+//     r_0 = z;  st_s = r_s + (E_s[idx_s] - r_s);  out = ((0 + st_0) + st_1) + ...;  r_{s+1} = r_s - st_s
+// can be recomputed bit-identically from z, the indices and the final codebooks.  This kernel does that in
+// one pass (read z, write out, S codeword gathers per element from L2) and also produces the S loss sums,
+// which removes the per-stage read-modify-write of the running sum from the stage kernels.
+// Same bulk-TMA tile pipeline as gather_bulk_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int CHAIN_MAX_S = 8;
+struct ChainArgs {
+  const float* E[CHAIN_MAX_S];
+  const int32_t* idx[CHAIN_MAX_S];
+  double* sse[CHAIN_MAX_S];
+  int K[CHAIN_MAX_S];
+  int S;
+};
+
+__global__ void __launch_bounds__(TILE_NT)
+rvq_chain_kernel(const float* __restrict__ z, ChainArgs ca, TileGeom g, float* __restrict__ out) {
+  using namespace ptx;
+  extern __shared__ __align__(128) float smem[];
+  __shared__ uint64_t full[BULK_STAGES];
+  __shared__ int s_off[256];
+  __shared__ int s_code[2][CHAIN_MAX_S][64];         // rows_per_tile <= 64 for this kernel
+  const int tid = threadIdx.x;
+  const int D = g.D, T = g.T, S = ca.S;
+  if (tid == 0) {
+    for (int s = 0; s < BULK_STAGES; ++s) mbar_init(smem_u32(full + s), 1);
+    fence_barrier_init();
+  }
+  if (tid < g.rows_per_tile) { const int b = tid / T, t = tid - b * T; s_off[tid] = b * D * T + t; }
+  __syncthreads();
+  const long long my_tiles = (g.ntiles > blockIdx.x) ? (g.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto tile_rows = [&](long long i) {
+    const long long r0 = (blockIdx.x + i * gridDim.x) * g.rows_per_tile;
+    return (int)min((long long)g.rows_per_tile, g.N - r0);
+  };
+  auto issue_load = [&](long long i) {
+    const int s = (int)(i % BULK_STAGES);
+    const long long r0 = (blockIdx.x + i * gridDim.x) * g.rows_per_tile;
+    const uint32_t bytes = (uint32_t)tile_rows(i) * D * 4;
+    mbar_expect_tx(smem_u32(full + s), bytes);
+    bulk_g2s(smem_u32(smem + (size_t)s * TILE_ELEMS), z + r0 * D, bytes, smem_u32(full + s));
+  };
+  auto load_codes = [&](long long i, int buf) {      // all threads: S x rows codes of tile i
+    const long long r0 = (blockIdx.x + i * gridDim.x) * g.rows_per_tile;
+    const int rows = tile_rows(i);
+    for (int e = tid; e < S * rows; e += TILE_NT) {
+      const int s = e / rows, r = e - s * rows;
+      const int k = __ldg(ca.idx[s] + r0 + r);
+      s_code[buf][s][r] = min(max(k, 0), ca.K[s] - 1);
+    }
+  };
+  if (tid == 0) for (long long i = 0; i < my_tiles && i < BULK_STAGES - 1; ++i) issue_load(i);
+  if (my_tiles > 0) load_codes(0, 0);
+  float part[CHAIN_MAX_S];
+#pragma unroll
+  for (int s = 0; s < CHAIN_MAX_S; ++s) part[s] = 0.f;
+  for (long long i = 0; i < my_tiles; ++i) {
+    const int st = (int)(i % BULK_STAGES);
+    const long long r0 = (blockIdx.x + i * gridDim.x) * g.rows_per_tile;
+    const int rows = tile_rows(i);
+    const int n = rows * D;
+    float* X = smem + (size_t)st * TILE_ELEMS;
+    if (tid == 0 && i + BULK_STAGES - 1 < my_tiles) {
+      bulk_wait_read<0>();
+      issue_load(i + BULK_STAGES - 1);
+    }
+    __syncthreads();                             // codes of this tile are in s_code[i & 1]
+    if (i + 1 < my_tiles) load_codes(i + 1, (int)((i + 1) & 1));
+    mbar_wait(smem_u32(full + st), (uint32_t)((i / BULK_STAGES) & 1), nullptr, 0);
+    const int (*code)[64] = s_code[i & 1];
+    constexpr int U = 4;
+    for (int e0 = tid; e0 < n; e0 += TILE_NT * U) {
+      int a[U], rr[U], kk[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * TILE_NT;
+        if (e < n) {
+          rr[u] = g.dshift >= 0 ? (e >> g.dshift) : (e / D);
+          kk[u] = e - rr[u] * D;
+          a[u] = s_off[rr[u]] + kk[u] * T;
+        } else { a[u] = -1; rr[u] = 0; kk[u] = 0; }
+      }
+      float q[U][CHAIN_MAX_S];
+#pragma unroll
+      for (int s = 0; s < CHAIN_MAX_S; ++s) {
+        if (s < S) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) q[u][s] = (a[u] >= 0) ? __ldg(ca.E[s] + (size_t)code[s][rr[u]] * D + kk[u]) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (a[u] < 0) continue;
+        float r = X[a[u]];
+        float acc = 0.f;
+#pragma unroll
+        for (int s = 0; s < CHAIN_MAX_S; ++s) {
+          if (s < S) {
+            const float diff = __fsub_rn(q[u][s], r);
+            const float stv = __fadd_rn(r, diff);
+            part[s] = fmaf(diff, diff, part[s]);
+            acc = __fadd_rn(acc, stv);
+            r = __fsub_rn(r, stv);
+          }
+        }
+        X[a[u]] = acc;
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(out + r0 * D, smem_u32(X), (uint32_t)n * 4);
+      bulk_commit();
+    }
+  }
+  if (tid == 0) bulk_wait_all<0>();
+  __shared__ double red[TILE_NT / 32];
+  for (int s = 0; s < S; ++s) {
+    double p = warp_sum((double)part[s]);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = p;
+    __syncthreads();
+    if (tid < 32) {
+      double v = tid < TILE_NT / 32 ? red[tid] : 0.0;
+      v = warp_sum(v);
+      if (tid == 0 && v != 0.0) atomicAdd(ca.sse[s], v);
+    }
+  }
+}
+
 // ema_accumulate on a tile: cnt via smem histogram, dw via 16-byte vector reductions
 __global__ void __launch_bounds__(TILE_NT)
 accumulate_tile_kernel(const float* __restrict__ z, const int32_t* __restrict__ idx, const float* __restrict__ E,
@@ -334,6 +467,30 @@ int try_gather_tile(const ZView& z, const float* E, const int32_t* idx, int K, i
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "gather_tile_kernel");
+  return 1;
+}
+
+// returns 1 if handled, 0 if the layout is not eligible
+int try_rvq_chain(const ZView& z, int S, const float* const* E, const int32_t* const* idx, const int* K,
+                  double* const* sse, float* out, cudaStream_t stream) {
+  TileGeom g;
+  if (S < 1 || S > CHAIN_MAX_S || !tile_geom(z, g)) return 0;
+  if (g.rows_per_tile > 64 || (g.rows_per_tile * g.D * 4) % 16 != 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return 0;
+  ChainArgs ca;
+  ca.S = S;
+  for (int s = 0; s < S; ++s) { ca.E[s] = E[s]; ca.idx[s] = idx[s]; ca.K[s] = K[s]; ca.sse[s] = sse[s]; }
+  for (int s = S; s < CHAIN_MAX_S; ++s) { ca.E[s] = nullptr; ca.idx[s] = nullptr; ca.K[s] = 1; ca.sse[s] = nullptr; }
+  const size_t smem = (size_t)BULK_STAGES * TILE_ELEMS * sizeof(float);
+  static thread_local bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(rvq_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(rvq_chain_kernel)");
+    configured = true;
+  }
+  rvq_chain_kernel<<<tile_grid(g, 4), TILE_NT, smem, stream>>>(z.p, ca, g, out);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "rvq_chain_kernel");
   return 1;
 }
 

@@ -184,16 +184,36 @@ class _RVQFn(torch.autograd.Function):
                         e0_snapshot = W.clone()       # a later call may update E_0 before backward runs
                 else:
                     check(lib.vqb200_vq_histogram(ptr(idx[s]), N, K, ptr(st.cnt), stream), "vq_histogram")
-                last = s == S - 1
-                plain = cfg.plain and S == 1
-                check(lib.vqb200_vq_gather_st(ptr(r), B, C, T, sB, sC, sT, ptr(W), ptr(idx[s]), K,
-                                              ptr(out) if plain else None,
-                                              None if last else ptr(residuals[s + 1]),
-                                              None if plain else ptr(out), 1 if s > 0 else 0,
-                                              ptr(st.sse), stream), "vq_gather_st")
-                check(lib.vqb200_vq_metrics(ptr(st.cnt), K, max(N * world, 1), ptr(st.sse), max(N * C, 1),
-                                            c_float(cfg.commitment_cost), 1 if cfg.use_ema else 0, ptr(m3[s]),
-                                            stream), "vq_metrics")
+                if cfg.plain and S == 1:
+                    # bare VectorQuantizer: out = st_0 itself (keeps the sign of zero of the reference's :63)
+                    check(lib.vqb200_vq_gather_st(ptr(r), B, C, T, sB, sC, sT, ptr(W), ptr(idx[s]), K, ptr(out),
+                                                  None, None, 0, ptr(st.sse), stream), "vq_gather_st")
+                    check(lib.vqb200_vq_metrics(ptr(st.cnt), K, max(N * world, 1), ptr(st.sse), max(N * C, 1),
+                                                c_float(cfg.commitment_cost), 1 if cfg.use_ema else 0, ptr(m3[s]),
+                                                stream), "vq_metrics")
+                elif s < S - 1:
+                    # next residual r_{s+1} = r_s - st_s (the running sum is rebuilt once, after the last stage)
+                    check(lib.vqb200_vq_gather_st(ptr(r), B, C, T, sB, sC, sT, ptr(W), ptr(idx[s]), K, None,
+                                                  ptr(residuals[s + 1]), None, 0, ptr(st.sse), stream), "vq_gather_st")
+            if not (cfg.plain and S == 1):
+                # all stages at once: out = ((0 + st_0) + st_1) + ... and the S loss sums, from z + indices + codebooks
+                import ctypes
+                Es = (ctypes.c_void_p * S)(*[weights[s].detach().data_ptr() for s in range(S)])
+                Is = (ctypes.c_void_p * S)(*[idx[s].data_ptr() for s in range(S)])
+                Ks = (ctypes.c_int64 * S)(*[weights[s].shape[0] for s in range(S)])
+                sse = torch.empty(S, dtype=torch.float64, device=dev)
+                sB, sC, sT = z.stride()
+                rc = lib.vqb200_rvq_output_chain(ptr(z), B, C, T, sB, sC, sT, S, Es, Is, Ks, ptr(out), ptr(sse), None, stream)
+                if rc == -5:        # VQB200_EWORKSPACE: arbitrary view, needs a running-residual scratch
+                    scratch = torch.empty((B, C, T), **f32)
+                    rc = lib.vqb200_rvq_output_chain(ptr(z), B, C, T, sB, sC, sT, S, Es, Is, Ks, ptr(out), ptr(sse),
+                                                     ptr(scratch), stream)
+                check(rc, "rvq_output_chain")
+                for s in range(S):
+                    st = cfg.states[s]
+                    check(lib.vqb200_vq_metrics(ptr(st.cnt), weights[s].shape[0], max(N * world, 1), ptr(sse[s:s + 1]),
+                                                max(N * C, 1), c_float(cfg.commitment_cost), 1 if cfg.use_ema else 0,
+                                                ptr(m3[s]), stream), "vq_metrics")
         if S == 1:
             loss, ppl, dcr = m3[0, 0], m3[0, 1], m3[0, 2]
             if not cfg.plain:

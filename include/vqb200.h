@@ -108,6 +108,17 @@ int vqb200_vq_gather_st(const float* z, int64_t B, int64_t C, int64_t T,
                         float* out, float* residual, float* accum, int accum_init,
                         double* sse, vqb200_stream_t stream);
 
+/* ---- RVQ output chain ---------------------------------- models/vqvae.py:94-98, all stages at once --
+ * Recomputes r_0 = z; st_s = r_s + (E_s[idx_s] - r_s); out = ((0 + st_0) + st_1) + ...; r_{s+1} = r_s - st_s
+ * from z, the S index arrays and the S (already updated) codebooks -- bit-identical to running the stages one
+ * after the other, because every codebook is updated once per step -- and the S loss sums
+ * sse[s] = sum (E_s[idx_s] - r_s)^2.  E / idx / K are HOST arrays of S device pointers / sizes.
+ * out: contiguous [B,C,T].  scratch (B*C*T floats) is only needed for non-contiguous views with S > 1. */
+int vqb200_rvq_output_chain(const float* z, int64_t B, int64_t C, int64_t T,
+                            int64_t sB, int64_t sC, int64_t sT,
+                            int32_t S, const float* const* E, const int32_t* const* idx, const int64_t* K,
+                            float* out, double* sse, float* scratch, vqb200_stream_t stream);
+
 /* ---- loss + metrics as device scalars ----------------- models/vqvae.py:55-61,66-74 (a7,a9) -
  * out3 = {loss, perplexity, dcr}.  loss = c*mse (EMA) or mse + c*mse (standard), mse = sse/numel;
  * perplexity = exp(-sum p log(p+1e-10)), p = cnt/N; dcr = 1 - #{cnt>0}/K. */
