@@ -195,33 +195,39 @@ gather_bulk_kernel(const float* __restrict__ z, const float* __restrict__ E, con
     __syncthreads();                             // s_code[i&1] written (previous iteration / prologue)
     mbar_wait(smem_u32(full + s), (uint32_t)((i / BULK_STAGES) & 1), nullptr, 0);
     const int* code = s_code[i & 1];
-    constexpr int U = 8;                         // codeword gathers in flight per thread (L2 latency hiding)
-    for (int e0 = tid; e0 < n; e0 += TILE_NT * U) {
-      int a[U]; float q[U];
+    // one thread = 4 consecutive dims of one row (16-byte codeword loads), U row-quads in flight per thread
+    constexpr int U = 4;
+    const int d4 = D >> 2, n4 = rows * d4;
+    for (int e0 = tid; e0 < n4; e0 += TILE_NT * U) {
+      int a[U]; float4 q[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int e = e0 + u * TILE_NT;
-        if (e < n) {
-          const int r = g.dshift >= 0 ? (e >> g.dshift) : (e / D);
-          const int k = e - r * D;
+        if (e < n4) {
+          const int r = e / d4, k = (e - r * d4) * 4;
           a[u] = s_off[r] + k * T;
-          q[u] = __ldg(E + (size_t)code[r] * D + k);
-        } else { a[u] = -1; q[u] = 0.f; }
+          q[u] = __ldg(reinterpret_cast<const float4*>(E + (size_t)code[r] * D + k));
+        } else { a[u] = -1; q[u] = make_float4(0.f, 0.f, 0.f, 0.f); }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (a[u] < 0) continue;
-        const float x = X[a[u]];
-        if (mode == GM_BACKWARD) {
-          X[a[u]] = fmaf(scale, __fsub_rn(x, q[u]), y_in ? Y[a[u]] : 0.f);
-        } else {
-          const float diff = __fsub_rn(q[u], x);
-          const float st = __fadd_rn(x, diff);
-          part = fmaf(diff, diff, part);
-          if (mode == GM_PLAIN) X[a[u]] = st;
-          else {
-            X[a[u]] = __fsub_rn(x, st);
-            if (TWO) Y[a[u]] = __fadd_rn(y_in ? Y[a[u]] : 0.f, st);
+        const float qv[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int ai = a[u] + c * T;
+          const float x = X[ai];
+          if (mode == GM_BACKWARD) {
+            X[ai] = fmaf(scale, __fsub_rn(x, qv[c]), y_in ? Y[ai] : 0.f);
+          } else {
+            const float diff = __fsub_rn(qv[c], x);
+            const float st = __fadd_rn(x, diff);
+            part = fmaf(diff, diff, part);
+            if (mode == GM_PLAIN) X[ai] = st;
+            else {
+              X[ai] = __fsub_rn(x, st);
+              if (TWO) Y[ai] = __fadd_rn(y_in ? Y[ai] : 0.f, st);
+            }
           }
         }
       }
@@ -323,42 +329,52 @@ rvq_chain_kernel(const float* __restrict__ z, ChainArgs ca, TileGeom g, float* _
     if (i + 1 < my_tiles) load_codes(i + 1, (int)((i + 1) & 1));
     mbar_wait(smem_u32(full + st), (uint32_t)((i / BULK_STAGES) & 1), nullptr, 0);
     const int (*code)[64] = s_code[i & 1];
-    constexpr int U = 4;
-    for (int e0 = tid; e0 < n; e0 += TILE_NT * U) {
+    // one thread = 4 consecutive dims of one row: codeword rows are fetched as 16-byte vectors (4x fewer
+    // load instructions), U row-quads in flight per thread to cover the L2 latency of the S gathers
+    constexpr int U = 2;
+    const int d4 = D >> 2, n4 = rows * d4;
+    for (int e0 = tid; e0 < n4; e0 += TILE_NT * U) {
       int a[U], rr[U], kk[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int e = e0 + u * TILE_NT;
-        if (e < n) {
-          rr[u] = g.dshift >= 0 ? (e >> g.dshift) : (e / D);
-          kk[u] = e - rr[u] * D;
+        if (e < n4) {
+          rr[u] = e / d4;
+          kk[u] = (e - rr[u] * d4) * 4;
           a[u] = s_off[rr[u]] + kk[u] * T;
         } else { a[u] = -1; rr[u] = 0; kk[u] = 0; }
       }
-      float q[U][CHAIN_MAX_S];
+      float4 q[U][CHAIN_MAX_S];
 #pragma unroll
       for (int s = 0; s < CHAIN_MAX_S; ++s) {
         if (s < S) {
 #pragma unroll
-          for (int u = 0; u < U; ++u) q[u][s] = (a[u] >= 0) ? __ldg(ca.E[s] + (size_t)code[s][rr[u]] * D + kk[u]) : 0.f;
+          for (int u = 0; u < U; ++u)
+            q[u][s] = (a[u] >= 0) ? __ldg(reinterpret_cast<const float4*>(ca.E[s] + (size_t)code[s][rr[u]] * D + kk[u]))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (a[u] < 0) continue;
-        float r = X[a[u]];
-        float acc = 0.f;
+        float r[4] = {X[a[u]], X[a[u] + T], X[a[u] + 2 * T], X[a[u] + 3 * T]};
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int s = 0; s < CHAIN_MAX_S; ++s) {
           if (s < S) {
-            const float diff = __fsub_rn(q[u][s], r);
-            const float stv = __fadd_rn(r, diff);
-            part[s] = fmaf(diff, diff, part[s]);
-            acc = __fadd_rn(acc, stv);
-            r = __fsub_rn(r, stv);
+            const float qv[4] = {q[u][s].x, q[u][s].y, q[u][s].z, q[u][s].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float diff = __fsub_rn(qv[c], r[c]);
+              const float stv = __fadd_rn(r[c], diff);
+              part[s] = fmaf(diff, diff, part[s]);
+              acc[c] = __fadd_rn(acc[c], stv);
+              r[c] = __fsub_rn(r[c], stv);
+            }
           }
         }
-        X[a[u]] = acc;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) X[a[u] + c * T] = acc[c];
       }
     }
     fence_proxy_async();
@@ -439,7 +455,7 @@ int try_gather_tile(const ZView& z, const float* E, const int32_t* idx, int K, i
   TileGeom g;
   if (!tile_geom(z, g)) return 0;
   if ((reinterpret_cast<uintptr_t>(o1) & 15) || (reinterpret_cast<uintptr_t>(o2) & 15) ||
-      (reinterpret_cast<uintptr_t>(in2) & 15) || (reinterpret_cast<uintptr_t>(E) & 3)) return 0;
+      (reinterpret_cast<uintptr_t>(in2) & 15) || (reinterpret_cast<uintptr_t>(E) & 15)) return 0;
   const bool two = (mode == GM_RVQ && o2) || (mode == GM_BACKWARD && in2);
   static const bool use_bulk = !(getenv("VQB200_NO_BULK") && atoi(getenv("VQB200_NO_BULK")));
   if (use_bulk && (g.rows_per_tile * g.D * 4) % 16 == 0) {
@@ -478,7 +494,10 @@ int try_rvq_chain(const ZView& z, int S, const float* const* E, const int32_t* c
   if (g.rows_per_tile > 64 || (g.rows_per_tile * g.D * 4) % 16 != 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return 0;
   ChainArgs ca;
   ca.S = S;
-  for (int s = 0; s < S; ++s) { ca.E[s] = E[s]; ca.idx[s] = idx[s]; ca.K[s] = K[s]; ca.sse[s] = sse[s]; }
+  for (int s = 0; s < S; ++s) {
+    if (reinterpret_cast<uintptr_t>(E[s]) & 15) return 0;
+    ca.E[s] = E[s]; ca.idx[s] = idx[s]; ca.K[s] = K[s]; ca.sse[s] = sse[s];
+  }
   for (int s = S; s < CHAIN_MAX_S; ++s) { ca.E[s] = nullptr; ca.idx[s] = nullptr; ca.K[s] = 1; ca.sse[s] = nullptr; }
   const size_t smem = (size_t)BULK_STAGES * TILE_ELEMS * sizeof(float);
   static thread_local bool configured = false;
