@@ -409,6 +409,48 @@ def test_strided_views_agree():
         assert q.is_contiguous()
 
 
+def test_rvq_strided_views_agree():
+    """ResidualVQ on arbitrary views (generic strided kernels + scratch-based output chain) must equal the
+    contiguous fast path bit for bit, in eval and in EMA training mode, forward and backward."""
+    import copy
+    vq = _mods()
+    S, K, D, B, Tt = 3, 128, 32, 41, 6
+    torch.manual_seed(0)
+    ref_mod = vq.ResidualVQ(S, K, D, use_ema=True).to(DEV)
+    with torch.no_grad():
+        for l in ref_mod.layers:
+            l.embedding.weight.normal_(0, 0.5); l.ema_w.copy_(l.embedding.weight); l.ema_cluster_size.fill_(1.0)
+    base = torch.randn(B, D, Tt, device=DEV)
+    g = torch.randn(B, D, Tt, device=DEV)
+    big = torch.zeros(B, D + 5, Tt + 3, device=DEV)
+    big[:, :D, :Tt] = base
+    views = {"contiguous": base.clone(),
+             "btc_permuted": base.permute(0, 2, 1).contiguous().permute(0, 2, 1),
+             "padded": big[:, :D, :Tt]}
+    results = {}
+    for name, v in views.items():
+        for train in (False, True):
+            m = copy.deepcopy(ref_mod).train(train)
+            x = v.detach().clone().as_strided(v.shape, v.stride()) if name == "contiguous" else v.detach()
+            x = x.requires_grad_(True)
+            loss, q, met = m(x)
+            torch.autograd.backward([q, loss], [g, torch.ones((), device=DEV)])
+            results[(name, train)] = (q.detach(), loss.detach(), m.last_indices.clone(), x.grad.detach().clone(),
+                                      m.layers[-1].embedding.weight.detach().clone())
+    for train in (False, True):
+        q0, l0, i0, g0, e0 = results[("contiguous", train)]
+        for name in ("btc_permuted", "padded"):
+            q, l, i, gz, e = results[(name, train)]
+            assert torch.equal(i, i0), (name, train)
+            if train:       # float-atomic order of the EMA sums differs between launches: last-bit differences in E
+                assert torch.allclose(q, q0, rtol=1e-5, atol=1e-6), (name, train)
+            else:
+                assert torch.equal(q, q0), (name, train)
+            assert torch.allclose(l, l0, rtol=1e-6), (name, train)
+            assert torch.allclose(gz, g0, rtol=1e-6, atol=1e-9), (name, train)
+            assert torch.allclose(e, e0, rtol=1e-5, atol=1e-7), (name, train)      # atomics order only
+
+
 @pytest.mark.parametrize("B,Tt", [(0, 10), (1, 1), (1, 10), (7, 3), (129, 1)])
 def test_ragged_and_empty(B, Tt):
     vq = _mods()
