@@ -34,6 +34,11 @@ _SIGNATURES = {
                                     _P, _P, c_int64, _P, _P, _P, c_int, _P, _P]),
     "vqb200_rvq_output_chain": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                         ctypes.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    "vqb200_rvq_small_eligible": (c_int, [c_int64, c_int64, ctypes.c_int32, _P]),
+    "vqb200_rvq_small_workspace_floats": (c_size_t, [ctypes.c_int32, _P]),
+    "vqb200_rvq_small_forward": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                         ctypes.c_int32, _P, _P, _P, _P, c_double, c_double, c_float, c_int, c_int,
+                                         _P, _P, _P, _P, _P, _P]),
     "vqb200_vq_metrics": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_float, c_int, _P, _P]),
     "vqb200_vq_backward_input": (c_int, [_P, c_int64, c_int64, c_int64,
                                          _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,

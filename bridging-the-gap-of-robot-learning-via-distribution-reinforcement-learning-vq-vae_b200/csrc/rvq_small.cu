@@ -1,0 +1,325 @@
+// vqb200 K4: single-launch ResidualVQ for the launch-bound shapes (BASELINE cfg2: 512 vectors, 4 x K=512).
+//
+// Replaces the whole Python loop of models/vqvae.py:94-100 (S x {distances, argmin, one-hot sums, EMA update,
+// gather, loss, metrics}, ~25 ATen launches per stage in the reference, 7 vqb200 launches per stage in the
+// multi-kernel path) by ONE kernel: a thread-block cluster of 8 CTAs owns the batch, keeps the running residual in
+// shared memory across all stages, and orders the stage phases
+//     assign + statistics  ->  EMA cluster sizes  ->  codebook update  ->  gather / residual / running sum
+// with cluster barriers (release/acquire at cluster scope), so the update-then-gather ordering of the reference
+// (:43-52) is kept without leaving the kernel.  Arithmetic is the exact fp32 formulation of assign_simt.cu
+// (d = fl(fl(|x|^2 + |E|^2) - 2 x.E), first minimum, NaN wins) and of ema.cu / gather.cu.
+// Eligible: D == 64, N <= 4096, K <= 4096, S <= 8, single process (no inter-GPU all-reduce inside the launch).
+#include <cooperative_groups.h>
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace vqb200 {
+namespace small {
+
+constexpr int D = 64;
+constexpr int CLUSTER = 8;
+constexpr int NT = 256;
+constexpr int MAX_S = 8;
+constexpr int MAX_K = 4096;
+constexpr int MAX_ROWS_PER_CTA = 512;           // N <= 4096
+constexpr int LDR = D + 1;                      // padded residual rows: conflict-free column walks
+
+struct Args {
+  ZView z;
+  int S;
+  int training_ema;                             // 1: EMA statistics + codebook update between assign and gather
+  int use_ema;                                  // loss formula: c*mse (EMA) vs mse + c*mse
+  float commitment;
+  float decay, one_minus_decay, eps;
+  float* E[MAX_S];
+  float* cs[MAX_S];
+  float* w[MAX_S];
+  float k_eps[MAX_S];
+  int K[MAX_S];
+  float* stats;                                 // [S][K_s*(D+1)] packed back to back (dw | cnt), zeroed in-kernel
+  float* scratch;                               // [S][K_s + 8]: normalised cluster sizes, n
+  double* sse;                                  // [S]
+  int32_t* idx;                                 // [S][N]
+  float* out;                                   // [B,C,T] contiguous
+  float* m3;                                    // [S][3] loss, perplexity, dcr
+};
+
+__device__ __forceinline__ long long stats_offset(const Args& a, int s) {
+  long long o = 0;
+  for (int i = 0; i < s; ++i) o += (long long)a.K[i] * (D + 1);
+  return o;
+}
+__device__ __forceinline__ long long scratch_offset(const Args& a, int s) {
+  long long o = 0;
+  for (int i = 0; i < s; ++i) o += a.K[i] + 8;
+  return o;
+}
+
+__global__ void __launch_bounds__(NT, 1)
+rvq_small_kernel(const Args a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) float smem[];
+  float* R = smem;                                        // [rows_c][LDR] running residual
+  float* ee = R + MAX_ROWS_PER_CTA * LDR;                 // [MAX_K] |E_k|^2 of the current stage
+  float* bestd = ee + MAX_K;                              // [8 warps][32]
+  int* bestk = reinterpret_cast<int*>(bestd + 8 * 32);    // [8 warps][32]
+  int* rowk = bestk + 8 * 32;                             // [MAX_ROWS_PER_CTA] code of each row (current stage)
+  __shared__ double red[8];
+  __shared__ float s_n;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster.block_rank();
+  const long long N = a.z.N;
+  const int rows_per = (int)((N + CLUSTER - 1) / CLUSTER);
+  const long long row0 = (long long)rank * rows_per;
+  const int rows = (int)max(0LL, min((long long)rows_per, N - row0));
+  const int C = (int)a.z.C, T = (int)a.z.T;
+
+  // ---- load this CTA's rows, zero the statistics of all stages ----
+  for (int i = tid; i < rows * D; i += NT) {
+    const int r = i / D, k = i - r * D;
+    R[r * LDR + k] = __ldg(a.z.p + a.z.row_base(row0 + r) + (long long)k * a.z.sC);
+  }
+  {
+    const long long total = stats_offset(a, a.S);
+    for (long long i = (long long)rank * NT + tid; i < total; i += (long long)CLUSTER * NT) a.stats[i] = 0.f;
+    if (rank == 0 && tid < a.S) a.sse[tid] = 0.0;
+  }
+  cluster.sync();
+
+  for (int s = 0; s < a.S; ++s) {
+    const int K = a.K[s];
+    float* __restrict__ E = a.E[s];
+    float* dw = a.stats + stats_offset(a, s);
+    float* cnt = dw + (long long)K * D;
+    float* cl = a.scratch + scratch_offset(a, s);
+
+    // ---- |E_k|^2 (sequential fp32 FMA chain per code, like the row dot products) ----
+    for (int k = tid; k < K; k += NT) {
+      const float4* e4 = reinterpret_cast<const float4*>(E + (size_t)k * D);
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < D / 4; ++c) {
+        const float4 v = e4[c];
+        acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+      }
+      ee[k] = acc;
+    }
+    __syncthreads();
+
+    // ---- K1: exact fp32 distances + argmin.  lane = row (held in 64 registers), warp w scans codes w, w+8, ... ----
+    for (int rb = 0; rb < rows; rb += 32) {
+      const int r = rb + lane;
+      float x[D];
+      float xx = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) { x[c] = (r < rows) ? R[r * LDR + c] : 0.f; xx = fmaf(x[c], x[c], xx); }
+      float bd = INFINITY; int bk = INT_MAX;
+      for (int k = warp; k < K; k += 8) {
+        const float4* e4 = reinterpret_cast<const float4*>(E + (size_t)k * D);   // warp-uniform address: broadcast
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < D / 4; ++c) {
+          const float4 v = e4[c];
+          dot = fmaf(x[4 * c], v.x, dot); dot = fmaf(x[4 * c + 1], v.y, dot);
+          dot = fmaf(x[4 * c + 2], v.z, dot); dot = fmaf(x[4 * c + 3], v.w, dot);
+        }
+        const float d = __fsub_rn(__fadd_rn(xx, ee[k]), __fmul_rn(2.0f, dot));
+        if (cand_better(d, k, bd, bk)) { bd = d; bk = k; }
+      }
+      bestd[warp * 32 + lane] = bd; bestk[warp * 32 + lane] = bk;
+      __syncthreads();
+      if (warp == 0 && r < rows) {
+#pragma unroll
+        for (int w8 = 1; w8 < 8; ++w8) {
+          const float od = bestd[w8 * 32 + lane]; const int ok = bestk[w8 * 32 + lane];
+          if (cand_better(od, ok, bd, bk)) { bd = od; bk = ok; }
+        }
+        rowk[r] = bk;
+        a.idx[(long long)s * N + row0 + r] = bk;
+      }
+      __syncthreads();
+    }
+
+    // ---- K3a: statistics (counts always: they feed perplexity / dcr) ----
+    for (int r = tid; r < rows; r += NT) atomicAdd(cnt + rowk[r], 1.0f);
+    if (a.training_ema) {
+      for (int i = tid; i < rows * (D / 4); i += NT) {
+        const int r = i / (D / 4), q = i - r * (D / 4);
+        const float* p = R + r * LDR + 4 * q;
+        red_add_v4(dw + (size_t)rowk[r] * D + 4 * q, p[0], p[1], p[2], p[3]);
+      }
+    }
+    if (a.training_ema) {
+      __threadfence();
+      cluster.sync();                                      // every CTA's statistics are in
+      // ---- K3b step 1 (cluster rank 0): cs <- decay*cs + (1-decay)*cnt ; n ; normalised cluster sizes ----
+      if (rank == 0) {
+        float* cs = a.cs[s];
+        double part = 0.0;
+        for (int k = tid; k < K; k += NT) {
+          const float v = fmaf(__ldcg(cnt + k), a.one_minus_decay, __fmul_rn(cs[k], a.decay));
+          cs[k] = v;
+          part += (double)v;
+        }
+        part = warp_sum(part);
+        if (lane == 0) red[warp] = part;
+        __syncthreads();
+        if (tid < 32) {
+          double v = tid < 8 ? red[tid] : 0.0;
+          v = warp_sum(v);
+          if (tid == 0) s_n = (float)v;
+        }
+        __syncthreads();
+        const float n = s_n;
+        for (int k = tid; k < K; k += NT)
+          cl[k] = __fmul_rn(__fdiv_rn(__fadd_rn(cs[k], a.eps), __fadd_rn(n, a.k_eps[s])), n);
+        __threadfence();
+      }
+      cluster.sync();
+      // ---- K3b step 2 (all CTAs, code slices): w <- decay*w + (1-decay)*dw ; E <- w / cluster ----
+      {
+        float* wv = a.w[s];
+        const int per = (K + CLUSTER - 1) / CLUSTER;
+        const int k0 = rank * per, k1 = min(K, k0 + per);
+        for (int i = k0 * D + tid; i < k1 * D; i += NT) {
+          const int k = i / D;
+          const float nw = fmaf(__ldcg(dw + i), a.one_minus_decay, __fmul_rn(wv[i], a.decay));
+          wv[i] = nw;
+          E[i] = __fdiv_rn(nw, __ldcg(cl + k));
+        }
+        __threadfence();
+      }
+      cluster.sync();                                      // the updated codebook is complete
+    }
+
+    // ---- K2: gather (post-update codebook), straight-through value, loss sum, running sum, next residual ----
+    float part = 0.f;
+    for (int i = tid; i < rows * D; i += NT) {
+      const int r = i / D, c = i - r * D;
+      const float x = R[r * LDR + c];
+      const float q = __ldcg(E + (size_t)rowk[r] * D + c);
+      const float diff = __fsub_rn(q, x);
+      const float st = __fadd_rn(x, diff);
+      part = fmaf(diff, diff, part);
+      const long long n = row0 + r;
+      const long long b = n / T; const int t = (int)(n - b * T);
+      float* o = a.out + (b * C + c) * T + t;
+      *o = __fadd_rn(s > 0 ? *o : 0.f, st);
+      R[r * LDR + c] = __fsub_rn(x, st);
+    }
+    {
+      double p = warp_sum((double)part);
+      __syncthreads();
+      if (lane == 0) red[warp] = p;
+      __syncthreads();
+      if (tid < 32) {
+        double v = tid < 8 ? red[tid] : 0.0;
+        v = warp_sum(v);
+        if (tid == 0 && v != 0.0) atomicAdd(a.sse + s, v);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- loss / perplexity / dcr of every stage (cluster rank 0, one warp per stage) ----
+  __threadfence();
+  cluster.sync();
+  if (rank == 0 && warp < a.S) {
+    const int s = warp;
+    const int K = a.K[s];
+    const float* cnt = a.stats + stats_offset(a, s) + (long long)K * D;
+    const float Nf = (float)N;
+    double ent = 0.0; int active = 0;
+    for (int k = lane; k < K; k += 32) {
+      const float c = __ldcg(cnt + k);
+      const float p = __fdiv_rn(c, Nf);
+      ent += (double)__fmul_rn(p, logf(__fadd_rn(p, 1e-10f)));
+      active += (c > 0.f);
+    }
+    ent = warp_sum(ent);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) active += __shfl_xor_sync(0xffffffffu, active, o);
+    if (lane == 0) {
+      const float mse = (float)(__ldcg(a.sse + s) / ((double)N * D));
+      a.m3[s * 3 + 0] = a.use_ema ? __fmul_rn(a.commitment, mse) : __fadd_rn(mse, __fmul_rn(a.commitment, mse));
+      a.m3[s * 3 + 1] = expf(-(float)ent);
+      a.m3[s * 3 + 2] = __fsub_rn(1.0f, __fdiv_rn((float)active, (float)K));
+    }
+  }
+}
+
+}  // namespace small
+}  // namespace vqb200
+
+using namespace vqb200;
+
+extern "C" {
+
+int vqb200_rvq_small_eligible(int64_t N, int64_t D, int32_t S, const int64_t* K) {
+  if (N < 1 || N > (int64_t)small::CLUSTER * small::MAX_ROWS_PER_CTA || D != small::D || S < 1 || S > small::MAX_S) return 0;
+  for (int s = 0; s < S; ++s) if (K[s] < 1 || K[s] > small::MAX_K) return 0;
+  return 1;
+}
+
+size_t vqb200_rvq_small_workspace_floats(int32_t S, const int64_t* K) {
+  size_t n = 0;
+  for (int s = 0; s < S; ++s) n += (size_t)K[s] * (small::D + 1) + (size_t)K[s] + 8;
+  return n + 16;
+}
+
+int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,
+                             int32_t S, float* const* E, float* const* ema_cluster_size, float* const* ema_w,
+                             const int64_t* K, double decay, double eps, float commitment_cost, int use_ema,
+                             int training, float* workspace, double* sse, int32_t* idx, float* out, float* m3,
+                             vqb200_stream_t stream_) {
+  using namespace small;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VQ_CHECK_ARG(z && E && K && workspace && sse && idx && out && m3, VQB200_EINVAL, "rvq_small_forward: null pointer");
+  VQ_CHECK_ARG(vqb200_rvq_small_eligible(B * T, C, S, K), VQB200_EUNSUPPORTED,
+               "rvq_small_forward: shape not eligible (needs D == 64, N <= 4096, K <= 4096, S <= 8)");
+  const int train_ema = (training && use_ema) ? 1 : 0;
+  VQ_CHECK_ARG(!train_ema || (ema_cluster_size && ema_w), VQB200_EINVAL, "rvq_small_forward: EMA buffers required");
+  Args a;
+  a.z = make_zview(z, B, C, T, sB, sC, sT);
+  a.S = S; a.training_ema = train_ema; a.use_ema = use_ema ? 1 : 0; a.commitment = commitment_cost;
+  a.decay = (float)decay; a.one_minus_decay = (float)(1.0 - decay); a.eps = (float)eps;
+  size_t stats_floats = 0;
+  for (int s = 0; s < S; ++s) {
+    VQ_CHECK_ARG(E[s] && (reinterpret_cast<uintptr_t>(E[s]) & 15) == 0, VQB200_EALIGN, "rvq_small_forward: codebook %d must be 16-byte aligned", s);
+    a.E[s] = E[s];
+    a.cs[s] = train_ema ? ema_cluster_size[s] : nullptr;
+    a.w[s] = train_ema ? ema_w[s] : nullptr;
+    VQ_CHECK_ARG(!train_ema || (a.cs[s] && a.w[s]), VQB200_EINVAL, "rvq_small_forward: EMA buffers of stage %d missing", s);
+    a.K[s] = (int)K[s];
+    a.k_eps[s] = (float)((double)K[s] * eps);
+    stats_floats += (size_t)K[s] * (D + 1);
+  }
+  for (int s = S; s < MAX_S; ++s) { a.E[s] = nullptr; a.cs[s] = nullptr; a.w[s] = nullptr; a.K[s] = 0; a.k_eps[s] = 0.f; }
+  VQ_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, VQB200_EALIGN, "rvq_small_forward: workspace must be 16-byte aligned");
+  a.stats = workspace;
+  a.scratch = workspace + ((stats_floats + 3) & ~(size_t)3);
+  a.sse = sse; a.idx = idx; a.out = out; a.m3 = m3;
+
+  const size_t smem = ((size_t)MAX_ROWS_PER_CTA * LDR + MAX_K + 8 * 32) * sizeof(float) + (8 * 32 + MAX_ROWS_PER_CTA) * sizeof(int);
+  static thread_local bool configured = false;
+  if (!configured) {
+    VQ_CUDA(cudaFuncSetAttribute(rvq_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CLUSTER);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  VQ_CUDA(cudaLaunchKernelEx(&cfg, rvq_small_kernel, a));
+  VQ_LAUNCH_CHECK("rvq_small_kernel");
+  return VQB200_OK;
+}
+
+}  // extern "C"

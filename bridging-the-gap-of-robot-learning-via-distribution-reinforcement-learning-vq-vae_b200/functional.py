@@ -155,14 +155,49 @@ class _RVQFn(torch.autograd.Function):
         ema_train = cfg.training and cfg.use_ema
         world = _dist.world_size() if ema_train else 1
         e0_snapshot = None
+        import ctypes
+        Ks = (ctypes.c_int64 * S)(*[weights[s].shape[0] for s in range(S)])
+        for s in range(S):
+            if weights[s].shape[1] != C:
+                raise RuntimeError(f"vqb200: channel dim {C} != embedding_dim {weights[s].shape[1]}")
+        # launch-bound shapes: the whole stage loop in ONE cluster kernel (csrc/rvq_small.cu).  Not for standard-VQ
+        # training (its codebook gradient needs the per-stage residuals) nor under data parallelism (the EMA
+        # statistics must cross GPUs between assignment and update).
+        fused = (cfg.algo == _lib.ASSIGN_AUTO and N > 0 and not _dist.enabled()
+                 and (cfg.use_ema or not any(ctx.needs_input_grad[2:]))
+                 and bool(lib.vqb200_rvq_small_eligible(N, C, S, Ks)))
+        if fused:
+            with torch.cuda.device(dev):
+                stream = stream_ptr(dev)
+                Wd = [weights[s].detach() for s in range(S)]
+                Es = (ctypes.c_void_p * S)(*[w.data_ptr() for w in Wd])
+                if ema_train:
+                    Cs = (ctypes.c_void_p * S)(*[cfg.ema_cluster_size[s].data_ptr() for s in range(S)])
+                    Ws = (ctypes.c_void_p * S)(*[cfg.ema_w[s].data_ptr() for s in range(S)])
+                else:
+                    Cs = Ws = None
+                st0 = cfg.states[0]
+                need = int(lib.vqb200_rvq_small_workspace_floats(S, Ks))
+                ws = getattr(st0, "_small_ws", None)
+                if ws is None or ws.numel() < need:
+                    ws = torch.empty(need, **f32)
+                    st0._small_ws = ws
+                sse = torch.empty(S, dtype=torch.float64, device=dev)
+                sB, sC, sT = z.stride()
+                check(lib.vqb200_rvq_small_forward(ptr(z), B, C, T, sB, sC, sT, S, Es, Cs, Ws, Ks, c_double(cfg.decay),
+                                                   c_double(cfg.eps), c_float(cfg.commitment_cost),
+                                                   1 if cfg.use_ema else 0, 1 if cfg.training else 0, ptr(ws), ptr(sse),
+                                                   ptr(idx), ptr(out), ptr(m3), stream), "rvq_small_forward")
+                for s in range(S):
+                    cfg.states[s].invalidate()      # |E|^2 / tile image were not refreshed by the fused kernel
+                if ema_train and ctx.needs_input_grad[0]:
+                    e0_snapshot = Wd[0].clone()
         with torch.cuda.device(dev):
             stream = stream_ptr(dev)
-            for s in range(S):
+            for s in range(S if not fused else 0):
                 st = cfg.states[s]
                 W = weights[s].detach()
                 K, D = W.shape
-                if D != C:
-                    raise RuntimeError(f"vqb200: channel dim {C} != embedding_dim {D}")
                 st.refresh(W)
                 r = residuals[s]
                 sB, sC, sT = r.stride()
@@ -180,7 +215,7 @@ class _RVQFn(torch.autograd.Function):
                                                   ptr(st.image), ptr(st.info), ptr(st.scratch), stream),
                           "ema_finalize")
                     st.mark_fresh(W)
-                    if s == 0 and z.requires_grad:
+                    if s == 0 and ctx.needs_input_grad[0]:
                         e0_snapshot = W.clone()       # a later call may update E_0 before backward runs
                 else:
                     check(lib.vqb200_vq_histogram(ptr(idx[s]), N, K, ptr(st.cnt), stream), "vq_histogram")
@@ -195,12 +230,10 @@ class _RVQFn(torch.autograd.Function):
                     # next residual r_{s+1} = r_s - st_s (the running sum is rebuilt once, after the last stage)
                     check(lib.vqb200_vq_gather_st(ptr(r), B, C, T, sB, sC, sT, ptr(W), ptr(idx[s]), K, None,
                                                   ptr(residuals[s + 1]), None, 0, ptr(st.sse), stream), "vq_gather_st")
-            if not (cfg.plain and S == 1):
+            if not fused and not (cfg.plain and S == 1):
                 # all stages at once: out = ((0 + st_0) + st_1) + ... and the S loss sums, from z + indices + codebooks
-                import ctypes
                 Es = (ctypes.c_void_p * S)(*[weights[s].detach().data_ptr() for s in range(S)])
                 Is = (ctypes.c_void_p * S)(*[idx[s].data_ptr() for s in range(S)])
-                Ks = (ctypes.c_int64 * S)(*[weights[s].shape[0] for s in range(S)])
                 sse = torch.empty(S, dtype=torch.float64, device=dev)
                 sB, sC, sT = z.stride()
                 rc = lib.vqb200_rvq_output_chain(ptr(z), B, C, T, sB, sC, sT, S, Es, Is, Ks, ptr(out), ptr(sse), None, stream)

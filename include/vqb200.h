@@ -119,6 +119,25 @@ int vqb200_rvq_output_chain(const float* z, int64_t B, int64_t C, int64_t T,
                             int32_t S, const float* const* E, const int32_t* const* idx, const int64_t* K,
                             float* out, double* sse, float* scratch, vqb200_stream_t stream);
 
+/* ---- K4: single-launch ResidualVQ for launch-bound shapes --- models/vqvae.py:87-108 (whole loop) ----
+ * One thread-block cluster (8 CTAs) runs ALL stages: exact fp32 assignment, EMA statistics, EMA finalize,
+ * gather / residual / running sum, loss + metrics, ordered by cluster barriers; the residual never leaves shared
+ * memory.  Eligible (vqb200_rvq_small_eligible): D == 64, N = B*T <= 4096, K_s <= 4096, S <= 8; single process
+ * only (no inter-GPU all-reduce inside the launch).  E / ema_cluster_size / ema_w / K are HOST arrays of S device
+ * pointers / sizes; codebooks and EMA buffers are updated in place when training && use_ema.
+ * workspace: vqb200_rvq_small_workspace_floats(S, K) floats (16-byte aligned); sse: S doubles;
+ * idx: int32 [S, N]; out: contiguous [B,C,T]; m3: [S,3] = {loss, perplexity, dcr} per stage.
+ * Derived codebook state (|E|^2, tile image) is NOT refreshed: call vqb200_codebook_prepare before the next
+ * vqb200_vq_assign on these codebooks. */
+int    vqb200_rvq_small_eligible(int64_t N, int64_t D, int32_t S, const int64_t* K);
+size_t vqb200_rvq_small_workspace_floats(int32_t S, const int64_t* K);
+int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T,
+                             int64_t sB, int64_t sC, int64_t sT,
+                             int32_t S, float* const* E, float* const* ema_cluster_size, float* const* ema_w,
+                             const int64_t* K, double decay, double eps, float commitment_cost, int use_ema,
+                             int training, float* workspace, double* sse, int32_t* idx, float* out, float* m3,
+                             vqb200_stream_t stream);
+
 /* ---- loss + metrics as device scalars ----------------- models/vqvae.py:55-61,66-74 (a7,a9) -
  * out3 = {loss, perplexity, dcr}.  loss = c*mse (EMA) or mse + c*mse (standard), mse = sse/numel;
  * perplexity = exp(-sum p log(p+1e-10)), p = cnt/N; dcr = 1 - #{cnt>0}/K. */
