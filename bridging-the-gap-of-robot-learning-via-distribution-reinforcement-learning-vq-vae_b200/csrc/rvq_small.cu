@@ -2,7 +2,7 @@
 //
 // Replaces the whole Python loop of models/vqvae.py:94-100 (S x {distances, argmin, one-hot sums, EMA update,
 // gather, loss, metrics}, ~25 ATen launches per stage in the reference, 7 vqb200 launches per stage in the
-// multi-kernel path) by ONE kernel: a thread-block cluster of 8 CTAs owns the batch, keeps the running residual in
+// multi-kernel path) by ONE kernel: a thread-block cluster of 16 CTAs (one GPC) owns the batch, keeps the running residual in
 // shared memory across all stages, and orders the stage phases
 //     assign + statistics  ->  EMA cluster sizes  ->  codebook update  ->  gather / residual / running sum
 // with cluster barriers (release/acquire at cluster scope), so the update-then-gather ordering of the reference
@@ -10,6 +10,7 @@
 // (d = fl(fl(|x|^2 + |E|^2) - 2 x.E), first minimum, NaN wins) and of ema.cu / gather.cu.
 // Eligible: D == 64, N <= 4096, K <= 4096, S <= 8, single process (no inter-GPU all-reduce inside the launch).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -18,12 +19,13 @@ namespace vqb200 {
 namespace small {
 
 constexpr int D = 64;
-constexpr int CLUSTER = 8;
+constexpr int CLUSTER = 16;                     // non-portable cluster size (one GPC), opt-in below
 constexpr int NT = 256;
 constexpr int MAX_S = 8;
 constexpr int MAX_K = 4096;
-constexpr int MAX_ROWS_PER_CTA = 512;           // N <= 4096
+constexpr int MAX_ROWS_PER_CTA = 256;           // N <= 4096
 constexpr int LDR = D + 1;                      // padded residual rows: conflict-free column walks
+constexpr int CHUNK = 128;                      // codes staged in shared memory per step (32 KiB)
 
 struct Args {
   ZView z;
@@ -43,6 +45,7 @@ struct Args {
   int32_t* idx;                                 // [S][N]
   float* out;                                   // [B,C,T] contiguous
   float* m3;                                    // [S][3] loss, perplexity, dcr
+  long long* dbg;                               // phase timestamps (development)
 };
 
 __device__ __forceinline__ long long stats_offset(const Args& a, int s) {
@@ -65,6 +68,7 @@ rvq_small_kernel(const Args a) {
   float* bestd = ee + MAX_K;                              // [8 warps][32]
   int* bestk = reinterpret_cast<int*>(bestd + 8 * 32);    // [8 warps][32]
   int* rowk = bestk + 8 * 32;                             // [MAX_ROWS_PER_CTA] code of each row (current stage)
+  float* Ech = reinterpret_cast<float*>(rowk + MAX_ROWS_PER_CTA);   // [CHUNK][D] staged codebook chunk (16-byte aligned)
   __shared__ double red[8];
   __shared__ float s_n;
 
@@ -75,6 +79,9 @@ rvq_small_kernel(const Args a) {
   const long long row0 = (long long)rank * rows_per;
   const int rows = (int)max(0LL, min((long long)rows_per, N - row0));
   const int C = (int)a.z.C, T = (int)a.z.T;
+  int dbg_i = 0;
+#define STAMP() do { if (a.dbg && rank == 0 && tid == 0 && dbg_i < 60) a.dbg[dbg_i++] = clock64(); } while (0)
+  STAMP();
 
   // ---- load this CTA's rows, zero the statistics of all stages ----
   for (int i = tid; i < rows * D; i += NT) {
@@ -87,6 +94,7 @@ rvq_small_kernel(const Args a) {
     if (rank == 0 && tid < a.S) a.sse[tid] = 0.0;
   }
   cluster.sync();
+  STAMP();
 
   for (int s = 0; s < a.S; ++s) {
     const int K = a.K[s];
@@ -95,53 +103,100 @@ rvq_small_kernel(const Args a) {
     float* cnt = dw + (long long)K * D;
     float* cl = a.scratch + scratch_offset(a, s);
 
-    // ---- |E_k|^2 (sequential fp32 FMA chain per code, like the row dot products) ----
-    for (int k = tid; k < K; k += NT) {
-      const float4* e4 = reinterpret_cast<const float4*>(E + (size_t)k * D);
-      float acc = 0.f;
+    // ---- K1: exact fp32 distances + argmin.  lane = row (held in 64 registers); the codebook is staged through
+    //      shared memory in 128-code chunks (coalesced loads, then warp-uniform broadcast reads); G warps share a
+    //      32-row block and split the codes of every chunk between them ----
+    {
+      const int nb = (rows + 31) >> 5;                                  // 32-row blocks of this CTA
+      const int G = nb <= 1 ? 8 : (nb == 2 ? 4 : (nb <= 4 ? 2 : 1));    // warps per row block
+      const int P = 8 / G;                                              // row blocks per pass
+      const int sub = warp % G;
+      for (int pass = 0; pass * P < max(nb, 1); ++pass) {
+        const int blk = pass * P + warp / G;
+        const int r = blk * 32 + lane;
+        const bool valid = blk < nb && r < rows;
+        float x[D];
+        float xx = 0.f;
 #pragma unroll
-      for (int c = 0; c < D / 4; ++c) {
-        const float4 v = e4[c];
-        acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
-      }
-      ee[k] = acc;
-    }
-    __syncthreads();
-
-    // ---- K1: exact fp32 distances + argmin.  lane = row (held in 64 registers), warp w scans codes w, w+8, ... ----
-    for (int rb = 0; rb < rows; rb += 32) {
-      const int r = rb + lane;
-      float x[D];
-      float xx = 0.f;
+        for (int c = 0; c < D; ++c) { x[c] = valid ? R[r * LDR + c] : 0.f; xx = fmaf(x[c], x[c], xx); }
+        float bd = INFINITY; int bk = INT_MAX;
+        for (int k0 = 0; k0 < K; k0 += CHUNK) {
+          const int kc = min(CHUNK, K - k0);
+          __syncthreads();                                              // previous chunk fully consumed
+          if (s == 0) STAMP();
+          {
+            // CHUNK*D/4 = 2048 float4 = 8 per thread: issue all loads before the first store (one L2 round trip)
+            const float4* src = reinterpret_cast<const float4*>(E + (size_t)k0 * D);
+            float4* dst = reinterpret_cast<float4*>(Ech);
+            const int n4 = kc * (D / 4);
+            float4 t[8];
 #pragma unroll
-      for (int c = 0; c < D; ++c) { x[c] = (r < rows) ? R[r * LDR + c] : 0.f; xx = fmaf(x[c], x[c], xx); }
-      float bd = INFINITY; int bk = INT_MAX;
-      for (int k = warp; k < K; k += 8) {
-        const float4* e4 = reinterpret_cast<const float4*>(E + (size_t)k * D);   // warp-uniform address: broadcast
-        float dot = 0.f;
+            for (int u = 0; u < 8; ++u) { const int i = tid + u * NT; if (i < n4) t[u] = src[i]; }
 #pragma unroll
-        for (int c = 0; c < D / 4; ++c) {
-          const float4 v = e4[c];
-          dot = fmaf(x[4 * c], v.x, dot); dot = fmaf(x[4 * c + 1], v.y, dot);
-          dot = fmaf(x[4 * c + 2], v.z, dot); dot = fmaf(x[4 * c + 3], v.w, dot);
+            for (int u = 0; u < 8; ++u) { const int i = tid + u * NT; if (i < n4) dst[i] = t[u]; }
+          }
+          __syncthreads();
+          if (s == 0) STAMP();
+          if (pass == 0) {
+            // |E_k|^2 of the chunk (needed once per stage): one code per thread, 16-byte reads rotated by the
+            // lane id so that the 32 rows a warp touches hit different banks
+            if (tid < kc) {
+              const float4* e4 = reinterpret_cast<const float4*>(Ech + tid * D);
+              float acc = 0.f;
+#pragma unroll
+              for (int c = 0; c < D / 4; ++c) {
+                const float4 v = e4[(c + lane) & (D / 4 - 1)];
+                acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+              }
+              ee[k0 + tid] = acc;
+            }
+            __syncthreads();
+            if (s == 0) STAMP();
+          }
+          if (blk < nb) {
+            // four codes per iteration: four independent FMA chains (each still sums dims 0..63 in order)
+            for (int kk = sub; kk < kc; kk += 4 * G) {
+              const float4* e0 = reinterpret_cast<const float4*>(Ech + kk * D);     // warp-uniform: broadcast
+              const float4* e1 = reinterpret_cast<const float4*>(Ech + min(kk + G, kc - 1) * D);
+              const float4* e2 = reinterpret_cast<const float4*>(Ech + min(kk + 2 * G, kc - 1) * D);
+              const float4* e3 = reinterpret_cast<const float4*>(Ech + min(kk + 3 * G, kc - 1) * D);
+              float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+              for (int c = 0; c < D / 4; ++c) {
+                const float4 v0 = e0[c], v1 = e1[c], v2 = e2[c], v3 = e3[c];
+                d0 = fmaf(x[4 * c], v0.x, d0); d1 = fmaf(x[4 * c], v1.x, d1); d2 = fmaf(x[4 * c], v2.x, d2); d3 = fmaf(x[4 * c], v3.x, d3);
+                d0 = fmaf(x[4 * c + 1], v0.y, d0); d1 = fmaf(x[4 * c + 1], v1.y, d1); d2 = fmaf(x[4 * c + 1], v2.y, d2); d3 = fmaf(x[4 * c + 1], v3.y, d3);
+                d0 = fmaf(x[4 * c + 2], v0.z, d0); d1 = fmaf(x[4 * c + 2], v1.z, d1); d2 = fmaf(x[4 * c + 2], v2.z, d2); d3 = fmaf(x[4 * c + 2], v3.z, d3);
+                d0 = fmaf(x[4 * c + 3], v0.w, d0); d1 = fmaf(x[4 * c + 3], v1.w, d1); d2 = fmaf(x[4 * c + 3], v2.w, d2); d3 = fmaf(x[4 * c + 3], v3.w, d3);
+              }
+              const float dots[4] = {d0, d1, d2, d3};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int kl = kk + u * G;
+                if (kl < kc) {
+                  const int k = k0 + kl;
+                  const float d = __fsub_rn(__fadd_rn(xx, ee[k]), __fmul_rn(2.0f, dots[u]));
+                  if (cand_better(d, k, bd, bk)) { bd = d; bk = k; }
+                }
+              }
+            }
+          }
         }
-        const float d = __fsub_rn(__fadd_rn(xx, ee[k]), __fmul_rn(2.0f, dot));
-        if (cand_better(d, k, bd, bk)) { bd = d; bk = k; }
-      }
-      bestd[warp * 32 + lane] = bd; bestk[warp * 32 + lane] = bk;
-      __syncthreads();
-      if (warp == 0 && r < rows) {
-#pragma unroll
-        for (int w8 = 1; w8 < 8; ++w8) {
-          const float od = bestd[w8 * 32 + lane]; const int ok = bestk[w8 * 32 + lane];
-          if (cand_better(od, ok, bd, bk)) { bd = od; bk = ok; }
+        bestd[warp * 32 + lane] = bd; bestk[warp * 32 + lane] = bk;
+        __syncthreads();
+        if (sub == 0 && valid) {
+          for (int g2 = 1; g2 < G; ++g2) {
+            const float od = bestd[(warp + g2) * 32 + lane]; const int ok = bestk[(warp + g2) * 32 + lane];
+            if (cand_better(od, ok, bd, bk)) { bd = od; bk = ok; }
+          }
+          rowk[r] = bk;
+          a.idx[(long long)s * N + row0 + r] = bk;
         }
-        rowk[r] = bk;
-        a.idx[(long long)s * N + row0 + r] = bk;
+        __syncthreads();
       }
-      __syncthreads();
     }
 
+    STAMP();
     // ---- K3a: statistics (counts always: they feed perplexity / dcr) ----
     for (int r = tid; r < rows; r += NT) atomicAdd(cnt + rowk[r], 1.0f);
     if (a.training_ema) {
@@ -154,6 +209,7 @@ rvq_small_kernel(const Args a) {
     if (a.training_ema) {
       __threadfence();
       cluster.sync();                                      // every CTA's statistics are in
+      STAMP();
       // ---- K3b step 1 (cluster rank 0): cs <- decay*cs + (1-decay)*cnt ; n ; normalised cluster sizes ----
       if (rank == 0) {
         float* cs = a.cs[s];
@@ -178,36 +234,69 @@ rvq_small_kernel(const Args a) {
         __threadfence();
       }
       cluster.sync();
+      STAMP();
       // ---- K3b step 2 (all CTAs, code slices): w <- decay*w + (1-decay)*dw ; E <- w / cluster ----
       {
         float* wv = a.w[s];
         const int per = (K + CLUSTER - 1) / CLUSTER;
         const int k0 = rank * per, k1 = min(K, k0 + per);
-        for (int i = k0 * D + tid; i < k1 * D; i += NT) {
-          const int k = i / D;
-          const float nw = fmaf(__ldcg(dw + i), a.one_minus_decay, __fmul_rn(wv[i], a.decay));
-          wv[i] = nw;
-          E[i] = __fdiv_rn(nw, __ldcg(cl + k));
+        // 16-byte vectors, two in flight per thread (the loads are independent: batch them ahead of the math)
+        const int q0 = k0 * (D / 4), q1 = k1 * (D / 4);
+        for (int i = q0 + tid; i < q1; i += 2 * NT) {
+          const int j = i + NT;
+          const bool two = j < q1;
+          const float4 d0 = __ldcg(reinterpret_cast<const float4*>(dw) + i);
+          const float4 w0 = reinterpret_cast<const float4*>(wv)[i];
+          const float c0 = __ldcg(cl + i / (D / 4));
+          const float4 d1 = two ? __ldcg(reinterpret_cast<const float4*>(dw) + j) : d0;
+          const float4 w1 = two ? reinterpret_cast<const float4*>(wv)[j] : w0;
+          const float c1 = two ? __ldcg(cl + j / (D / 4)) : c0;
+          float4 n0, n1, e0, e1;
+          n0.x = fmaf(d0.x, a.one_minus_decay, __fmul_rn(w0.x, a.decay)); n0.y = fmaf(d0.y, a.one_minus_decay, __fmul_rn(w0.y, a.decay));
+          n0.z = fmaf(d0.z, a.one_minus_decay, __fmul_rn(w0.z, a.decay)); n0.w = fmaf(d0.w, a.one_minus_decay, __fmul_rn(w0.w, a.decay));
+          n1.x = fmaf(d1.x, a.one_minus_decay, __fmul_rn(w1.x, a.decay)); n1.y = fmaf(d1.y, a.one_minus_decay, __fmul_rn(w1.y, a.decay));
+          n1.z = fmaf(d1.z, a.one_minus_decay, __fmul_rn(w1.z, a.decay)); n1.w = fmaf(d1.w, a.one_minus_decay, __fmul_rn(w1.w, a.decay));
+          e0 = make_float4(__fdiv_rn(n0.x, c0), __fdiv_rn(n0.y, c0), __fdiv_rn(n0.z, c0), __fdiv_rn(n0.w, c0));
+          e1 = make_float4(__fdiv_rn(n1.x, c1), __fdiv_rn(n1.y, c1), __fdiv_rn(n1.z, c1), __fdiv_rn(n1.w, c1));
+          reinterpret_cast<float4*>(wv)[i] = n0; reinterpret_cast<float4*>(E)[i] = e0;
+          if (two) { reinterpret_cast<float4*>(wv)[j] = n1; reinterpret_cast<float4*>(E)[j] = e1; }
         }
         __threadfence();
       }
       cluster.sync();                                      // the updated codebook is complete
+      STAMP();
     }
 
     // ---- K2: gather (post-update codebook), straight-through value, loss sum, running sum, next residual ----
     float part = 0.f;
-    for (int i = tid; i < rows * D; i += NT) {
-      const int r = i / D, c = i - r * D;
-      const float x = R[r * LDR + c];
-      const float q = __ldcg(E + (size_t)rowk[r] * D + c);
-      const float diff = __fsub_rn(q, x);
-      const float st = __fadd_rn(x, diff);
-      part = fmaf(diff, diff, part);
-      const long long n = row0 + r;
-      const long long b = n / T; const int t = (int)(n - b * T);
-      float* o = a.out + (b * C + c) * T + t;
-      *o = __fadd_rn(s > 0 ? *o : 0.f, st);
-      R[r * LDR + c] = __fsub_rn(x, st);
+    {
+      constexpr int U = 4;                                 // independent codeword / running-sum loads in flight
+      for (int i0 = tid; i0 < rows * D; i0 += NT * U) {
+        float q[U], prev[U]; float* op[U]; int ri[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * NT;
+          if (i < rows * D) {
+            const int r = i / D, c = i - r * D;
+            ri[u] = r * LDR + c;
+            q[u] = __ldcg(E + (size_t)rowk[r] * D + c);
+            const long long n = row0 + r;
+            const long long b = n / T; const int t = (int)(n - b * T);
+            op[u] = a.out + (b * C + c) * T + t;
+            prev[u] = s > 0 ? *op[u] : 0.f;
+          } else { ri[u] = -1; q[u] = 0.f; op[u] = nullptr; prev[u] = 0.f; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (ri[u] < 0) continue;
+          const float x = R[ri[u]];
+          const float diff = __fsub_rn(q[u], x);
+          const float st = __fadd_rn(x, diff);
+          part = fmaf(diff, diff, part);
+          *op[u] = __fadd_rn(prev[u], st);
+          R[ri[u]] = __fsub_rn(x, st);
+        }
+      }
     }
     {
       double p = warp_sum((double)part);
@@ -221,6 +310,7 @@ rvq_small_kernel(const Args a) {
       }
     }
     __syncthreads();
+    STAMP();
   }
 
   // ---- loss / perplexity / dcr of every stage (cluster rank 0, one warp per stage) ----
@@ -232,11 +322,16 @@ rvq_small_kernel(const Args a) {
     const float* cnt = a.stats + stats_offset(a, s) + (long long)K * D;
     const float Nf = (float)N;
     double ent = 0.0; int active = 0;
-    for (int k = lane; k < K; k += 32) {
-      const float c = __ldcg(cnt + k);
-      const float p = __fdiv_rn(c, Nf);
-      ent += (double)__fmul_rn(p, logf(__fadd_rn(p, 1e-10f)));
-      active += (c > 0.f);
+    for (int k0 = 0; k0 < K; k0 += 32 * 8) {
+      float c8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int k = k0 + u * 32 + lane; c8[u] = (k < K) ? __ldcg(cnt + k) : 0.f; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float p = __fdiv_rn(c8[u], Nf);
+        ent += (double)__fmul_rn(p, logf(__fadd_rn(p, 1e-10f)));
+        active += (c8[u] > 0.f);
+      }
     }
     ent = warp_sum(ent);
 #pragma unroll
@@ -248,6 +343,8 @@ rvq_small_kernel(const Args a) {
       a.m3[s * 3 + 2] = __fsub_rn(1.0f, __fdiv_rn((float)active, (float)K));
     }
   }
+  __syncthreads();
+  STAMP();
 }
 
 }  // namespace small
@@ -266,7 +363,7 @@ int vqb200_rvq_small_eligible(int64_t N, int64_t D, int32_t S, const int64_t* K)
 size_t vqb200_rvq_small_workspace_floats(int32_t S, const int64_t* K) {
   size_t n = 0;
   for (int s = 0; s < S; ++s) n += (size_t)K[s] * (small::D + 1) + (size_t)K[s] + 8;
-  return n + 16;
+  return n + 16 + 256;
 }
 
 int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,
@@ -301,11 +398,17 @@ int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, in
   a.stats = workspace;
   a.scratch = workspace + ((stats_floats + 3) & ~(size_t)3);
   a.sse = sse; a.idx = idx; a.out = out; a.m3 = m3;
+  {
+    size_t sc = 0; for (int s = 0; s < S; ++s) sc += (size_t)K[s] + 8;
+    a.dbg = getenv("VQB200_SMALL_DEBUG") ? reinterpret_cast<long long*>(a.scratch + ((sc + 3) & ~(size_t)3) + 4) : nullptr;
+  }
 
-  const size_t smem = ((size_t)MAX_ROWS_PER_CTA * LDR + MAX_K + 8 * 32) * sizeof(float) + (8 * 32 + MAX_ROWS_PER_CTA) * sizeof(int);
+  const size_t smem = ((size_t)MAX_ROWS_PER_CTA * LDR + MAX_K + 8 * 32 + (size_t)CHUNK * D) * sizeof(float) +
+                      (8 * 32 + MAX_ROWS_PER_CTA) * sizeof(int);
   static thread_local bool configured = false;
   if (!configured) {
     VQ_CUDA(cudaFuncSetAttribute(rvq_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VQ_CUDA(cudaFuncSetAttribute(rvq_small_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     configured = true;
   }
   cudaLaunchConfig_t cfg = {};

@@ -120,7 +120,7 @@ int vqb200_rvq_output_chain(const float* z, int64_t B, int64_t C, int64_t T,
                             float* out, double* sse, float* scratch, vqb200_stream_t stream);
 
 /* ---- K4: single-launch ResidualVQ for launch-bound shapes --- models/vqvae.py:87-108 (whole loop) ----
- * One thread-block cluster (8 CTAs) runs ALL stages: exact fp32 assignment, EMA statistics, EMA finalize,
+ * One thread-block cluster (16 CTAs) runs ALL stages: exact fp32 assignment, EMA statistics, EMA finalize,
  * gather / residual / running sum, loss + metrics, ordered by cluster barriers; the residual never leaves shared
  * memory.  Eligible (vqb200_rvq_small_eligible): D == 64, N = B*T <= 4096, K_s <= 4096, S <= 8; single process
  * only (no inter-GPU all-reduce inside the launch).  E / ema_cluster_size / ema_w / K are HOST arrays of S device
