@@ -274,6 +274,7 @@ struct ChainArgs {
   int S;
 };
 
+template <int S>
 __global__ void __launch_bounds__(TILE_NT)
 rvq_chain_kernel(const float* __restrict__ z, ChainArgs ca, TileGeom g, float* __restrict__ out) {
   using namespace ptx;
@@ -282,7 +283,7 @@ rvq_chain_kernel(const float* __restrict__ z, ChainArgs ca, TileGeom g, float* _
   __shared__ int s_off[256];
   __shared__ int s_code[2][CHAIN_MAX_S][64];         // rows_per_tile <= 64 for this kernel
   const int tid = threadIdx.x;
-  const int D = g.D, T = g.T, S = ca.S;
+  const int D = g.D, T = g.T;
   if (tid == 0) {
     for (int s = 0; s < BULK_STAGES; ++s) mbar_init(smem_u32(full + s), 1);
     fence_barrier_init();
@@ -312,9 +313,9 @@ rvq_chain_kernel(const float* __restrict__ z, ChainArgs ca, TileGeom g, float* _
   };
   if (tid == 0) for (long long i = 0; i < my_tiles && i < BULK_STAGES - 1; ++i) issue_load(i);
   if (my_tiles > 0) load_codes(0, 0);
-  float part[CHAIN_MAX_S];
+  float part[S];
 #pragma unroll
-  for (int s = 0; s < CHAIN_MAX_S; ++s) part[s] = 0.f;
+  for (int s = 0; s < S; ++s) part[s] = 0.f;
   for (long long i = 0; i < my_tiles; ++i) {
     const int st = (int)(i % BULK_STAGES);
     const long long r0 = (blockIdx.x + i * gridDim.x) * g.rows_per_tile;
@@ -331,7 +332,7 @@ rvq_chain_kernel(const float* __restrict__ z, ChainArgs ca, TileGeom g, float* _
     const int (*code)[64] = s_code[i & 1];
     // one thread = 4 consecutive dims of one row: codeword rows are fetched as 16-byte vectors (4x fewer
     // load instructions), U row-quads in flight per thread to cover the L2 latency of the S gathers
-    constexpr int U = 2;
+    constexpr int U = (S <= 2) ? 4 : ((S <= 4) ? 3 : 2);
     const int d4 = D >> 2, n4 = rows * d4;
     for (int e0 = tid; e0 < n4; e0 += TILE_NT * U) {
       int a[U], rr[U], kk[U];
@@ -344,15 +345,13 @@ rvq_chain_kernel(const float* __restrict__ z, ChainArgs ca, TileGeom g, float* _
           a[u] = s_off[rr[u]] + kk[u] * T;
         } else { a[u] = -1; rr[u] = 0; kk[u] = 0; }
       }
-      float4 q[U][CHAIN_MAX_S];
+      float4 q[U][S];
 #pragma unroll
-      for (int s = 0; s < CHAIN_MAX_S; ++s) {
-        if (s < S) {
+      for (int s = 0; s < S; ++s) {
 #pragma unroll
-          for (int u = 0; u < U; ++u)
-            q[u][s] = (a[u] >= 0) ? __ldg(reinterpret_cast<const float4*>(ca.E[s] + (size_t)code[s][rr[u]] * D + kk[u]))
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int u = 0; u < U; ++u)
+          q[u][s] = (a[u] >= 0) ? __ldg(reinterpret_cast<const float4*>(ca.E[s] + (size_t)code[s][rr[u]] * D + kk[u]))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -360,17 +359,15 @@ rvq_chain_kernel(const float* __restrict__ z, ChainArgs ca, TileGeom g, float* _
         float r[4] = {X[a[u]], X[a[u] + T], X[a[u] + 2 * T], X[a[u] + 3 * T]};
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int s = 0; s < CHAIN_MAX_S; ++s) {
-          if (s < S) {
-            const float qv[4] = {q[u][s].x, q[u][s].y, q[u][s].z, q[u][s].w};
+        for (int s = 0; s < S; ++s) {
+          const float qv[4] = {q[u][s].x, q[u][s].y, q[u][s].z, q[u][s].w};
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const float diff = __fsub_rn(qv[c], r[c]);
-              const float stv = __fadd_rn(r[c], diff);
-              part[s] = fmaf(diff, diff, part[s]);
-              acc[c] = __fadd_rn(acc[c], stv);
-              r[c] = __fsub_rn(r[c], stv);
-            }
+          for (int c = 0; c < 4; ++c) {
+            const float diff = __fsub_rn(qv[c], r[c]);
+            const float stv = __fadd_rn(r[c], diff);
+            part[s] = fmaf(diff, diff, part[s]);
+            acc[c] = __fadd_rn(acc[c], stv);
+            r[c] = __fsub_rn(r[c], stv);
           }
         }
 #pragma unroll
@@ -500,13 +497,25 @@ int try_rvq_chain(const ZView& z, int S, const float* const* E, const int32_t* c
   }
   for (int s = S; s < CHAIN_MAX_S; ++s) { ca.E[s] = nullptr; ca.idx[s] = nullptr; ca.K[s] = 1; ca.sse[s] = nullptr; }
   const size_t smem = (size_t)BULK_STAGES * TILE_ELEMS * sizeof(float);
-  static thread_local bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(rvq_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(rvq_chain_kernel)");
-    configured = true;
+  const int grid = tile_grid(g, 4);
+  auto launch = [&](auto kernel) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, TILE_NT, smem, stream>>>(z.p, ca, g, out);
+    return cudaSuccess;
+  };
+  cudaError_t le = cudaSuccess;
+  switch (S) {
+    case 1: le = launch(rvq_chain_kernel<1>); break;
+    case 2: le = launch(rvq_chain_kernel<2>); break;
+    case 3: le = launch(rvq_chain_kernel<3>); break;
+    case 4: le = launch(rvq_chain_kernel<4>); break;
+    case 5: le = launch(rvq_chain_kernel<5>); break;
+    case 6: le = launch(rvq_chain_kernel<6>); break;
+    case 7: le = launch(rvq_chain_kernel<7>); break;
+    default: le = launch(rvq_chain_kernel<8>); break;
   }
-  rvq_chain_kernel<<<tile_grid(g, 4), TILE_NT, smem, stream>>>(z.p, ca, g, out);
+  if (le != cudaSuccess) return cuda_fail(le, "rvq_chain_kernel setup");
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "rvq_chain_kernel");
