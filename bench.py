@@ -447,15 +447,20 @@ def run_extras(torch, vqb200, dev, peaks):
         res["cfg4_lfq_elementwise_n10m"] = {"vectors_per_s": n / (ms * 1e-3), "GBps_algorithmic": n * 88 / (ms * 1e-3) / 1e9,
                                             "frac_of_hbm": n * 88 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
         del ze, zl
-        # cfg5 point: EMA-VQ K=4096, D=128, N = 4 M (assignment only + full step)
-        cfg = WORKLOADS["cfg5_ema_k4096_d128"]
-        mod5, layers5 = build_module(vqb200, torch, cfg, dev)
-        z5 = torch.randn(cfg["B"], cfg["D"], 1, device=dev)
-        st5 = layers5[0]._state(dev)
-        ms = timeit(lambda: vqb200.vq_assign(z5, layers5[0].embedding.weight, st5), 2, warm=1)
-        fl = 2.0 * cfg["B"] * cfg["K"] * cfg["D"]
-        res["cfg5_assign_k4096_d128_n4m"] = {"ms": ms, "vectors_per_s": cfg["B"] / (ms * 1e-3), "TFLOPs": fl / (ms * 1e-3) / 1e12,
-                                             "frac_of_bf16_peak": fl / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"]}
+        # cfg5 sweep points (assignment kernel K1 alone; N bounded so that the default run stays short).
+        # D = 64 / 128 / 256 run the tcgen05 path, D = 512 the exact CUDA-core path.
+        for (K5, D5, N5) in ((512, 64, 4_194_304), (4096, 64, 2_097_152), (16384, 64, 1_048_576), (65536, 64, 262_144),
+                            (4096, 128, 1_048_576), (4096, 256, 524_288), (4096, 512, 65_536)):
+            torch.manual_seed(5)
+            w5 = torch.randn(K5, D5, device=dev)
+            z5 = torch.randn(N5, D5, 1, device=dev)
+            st5 = vqb200.QuantizerState(K5, D5, dev)
+            ms = timeit(lambda: vqb200.vq_assign(z5, w5, st5), 3, warm=2)
+            fl = 2.0 * N5 * K5 * D5
+            res[f"cfg5_assign_k{K5}_d{D5}"] = {"n": N5, "ms": ms, "vectors_per_s": N5 / (ms * 1e-3),
+                                               "TFLOPs": fl / (ms * 1e-3) / 1e12,
+                                               "frac_of_bf16_peak": fl / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"]}
+            del w5, z5, st5
     except Exception as ex:  # pragma: no cover
         res["error"] = repr(ex)
     return res

@@ -20,12 +20,14 @@ from . import _lib
 from .functional import (QuantizerState, RVQConfig, rvq_quantize, fsq_round, lfq_sign)
 
 
-def _require_cuda(z: torch.Tensor, who: str) -> None:
+def _require_cuda(z: torch.Tensor, who: str) -> torch.Tensor:
     if not isinstance(z, torch.Tensor) or not z.is_cuda:
         raise RuntimeError(f"{who}: input must be a CUDA tensor -- vqb200 has no CPU fallback "
                            "(the reference's CPU path lives in /root/reference, the test oracle in oracle/)")
     if z.dim() != 3:
         raise RuntimeError(f"{who}: expected [B, C, T], got {tuple(z.shape)}")
+    # the kernels compute in fp32 like the reference; a half / bf16 latent (autocast) is widened differentiably
+    return z if z.dtype == torch.float32 else z.float()
 
 
 class VectorQuantizer(nn.Module):
@@ -74,7 +76,7 @@ class VectorQuantizer(nn.Module):
                          self.training, plain, self.assign_algo)
 
     def forward(self, inputs):
-        _require_cuda(inputs, "VectorQuantizer")
+        inputs = _require_cuda(inputs, "VectorQuantizer")
         w = self.embedding.weight
         if w.device != inputs.device:
             raise RuntimeError("VectorQuantizer: module and input live on different devices")
@@ -94,7 +96,7 @@ class ResidualVQ(nn.Module):
         self.last_indices: Optional[torch.Tensor] = None
 
     def forward(self, x):
-        _require_cuda(x, "ResidualVQ")
+        x = _require_cuda(x, "ResidualVQ")
         layers: List[VectorQuantizer] = list(self.layers)
         if not layers:
             raise RuntimeError("ResidualVQ: no quantizer layers")
@@ -131,7 +133,7 @@ class FSQ(nn.Module):
         self.last_indices: Optional[torch.Tensor] = None
 
     def forward(self, z):
-        _require_cuda(z, "FSQ")
+        z = _require_cuda(z, "FSQ")
         z_e = self.project_in(z)                                       # [B, d, T]
         z_hard, idx, m2 = fsq_round(z_e, self._basis, self.codebook_size)
         z_out = self.project_out(z_hard)
@@ -155,7 +157,7 @@ class LFQ(nn.Module):
         self.last_indices: Optional[torch.Tensor] = None
 
     def forward(self, z):
-        _require_cuda(z, "LFQ")
+        z = _require_cuda(z, "LFQ")
         z_e = self.project_in(z)
         z_q, loss, idx, m3 = lfq_sign(z_e, self.entropy_loss_weight)
         out = self.project_out(z_q)
@@ -173,7 +175,7 @@ class HybridVQ(nn.Module):
                              commitment_cost=0.25, use_ema=True)
 
     def forward(self, z):
-        _require_cuda(z, "HybridVQ")
+        z = _require_cuda(z, "HybridVQ")
         _, z_fsq, m_fsq = self.fsq(z)
         residual = z - z_fsq
         loss_vq, z_vq, m_vq = self.vq(residual)
