@@ -24,7 +24,7 @@ using namespace vqb200;
 extern "C" {
 
 size_t vqb200_assign_workspace_bytes(int64_t N, int64_t D) {
-  if (D == 128 || D == 256) return assign_tc_gen_workspace_bytes(N, (int)D);
+  if (D == 128 || D == 256 || D == 512) return assign_tc_gen_workspace_bytes(N, (int)D);
   return assign_tc_workspace_bytes(N);
 }
 
@@ -47,7 +47,7 @@ int vqb200_vq_assign(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB
   if (algo == VQB200_ASSIGN_TC) {
     VQ_CHECK_ARG(image && info && workspace, VQB200_EINVAL, "vq_assign(TC): image, info and workspace are required");
     VQ_CHECK_ARG(!best, VQB200_EUNSUPPORTED, "vq_assign(TC): the winning distance is only produced by the SIMT algorithm");
-    VQ_CHECK_ARG(eligible, VQB200_EUNSUPPORTED, "vq_assign(TC): shape K=%lld D=%d not eligible (D must be 64, 128 or 256)", (long long)K, D);
+    VQ_CHECK_ARG(eligible, VQB200_EUNSUPPORTED, "vq_assign(TC): shape K=%lld D=%d not eligible (D must be 64, 128, 256 or 512)", (long long)K, D);
     use_tc = true;
   } else if (algo == VQB200_ASSIGN_AUTO) {
     use_tc = image && info && workspace && !best && eligible && workspace_bytes >= need && zv.N >= 2048;

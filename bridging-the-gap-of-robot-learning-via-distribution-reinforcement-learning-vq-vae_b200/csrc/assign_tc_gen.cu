@@ -1,4 +1,4 @@
-// vqb200 K1 (tensor-core variant for D = 128 / 256): fused distance + argmin on tcgen05 / TMEM / bulk-TMA.
+// vqb200 K1 (tensor-core variant for D = 128 / 256 / 512): fused distance + argmin on tcgen05 / TMEM / bulk-TMA.
 //
 // Same exactness scheme as assign_tc.cu (split-bf16 filter + proven margin + exact fallback list), for the
 // wider embedding dims of BASELINE cfg5.  A row no longer fits a register file for an in-place conversion, so the
@@ -9,7 +9,8 @@
 //              (code tile j, dim block kb) through a 3-stage ring + 512 B of -|E|^2/2 per code tile
 //   warp 1     TMEM allocator + single-thread tcgen05.mma issuer: per code tile 12*KB MMAs (M=128, N=128, K=16)
 //   warps 2-5  epilogue: tcgen05.ld, running top-2 with packed index (tc_common.cuh), margin test
-// At D >= 128 the MMAs (3 split products) outweigh the TMEM drain, so four epilogue warps suffice.
+// At D >= 128 the MMAs (3 split products) outweigh the TMEM drain.  D = 512: the A operand of a row tile (256 KiB)
+// no longer fits, so its 64-dim blocks are streamed through the ring next to the codebook tiles (STREAM_A).
 #include "common.cuh"
 #include "codebook.cuh"
 #include "tc_common.cuh"
@@ -34,25 +35,35 @@ constexpr int SMEM_XCH = TILE_M * 16;                // per-row (g1, g2, gi) han
 // image tile (row tile rt, dim block kb) at byte offset (rt*KB + kb) * 32768: 16 KiB hi then 16 KiB lo,
 // row r = 128 bytes, 16-byte chunk j at position j ^ (r & 7).  Rows >= N are zero.
 __global__ void __launch_bounds__(256)
-z_image_kernel(ZView z, int D, int KB, unsigned char* __restrict__ image, long long n_row_tiles) {
-  extern __shared__ __align__(16) float tile[];       // [128][D + 4]
+z_image_kernel(ZView z, int D, int KB, int sub_rows, unsigned char* __restrict__ image, float* __restrict__ xnorm2,
+               long long n_row_tiles) {
+  extern __shared__ __align__(16) float tile[];       // [sub_rows][D + 4]
   const int LD = D + 4;
   const int tid = threadIdx.x;
-  for (long long rt = blockIdx.x; rt < n_row_tiles; rt += gridDim.x) {
-    const long long n0 = rt * TILE_M;
-    const int rows = (int)min((long long)TILE_M, z.N - n0);
+  const int subs = TILE_M / sub_rows;                 // 128-row image tiles are filled in `subs` passes
+  for (long long it = blockIdx.x; it < n_row_tiles * subs; it += gridDim.x) {
+    const long long rt = it / subs;
+    const int r_base = (int)(it - rt * subs) * sub_rows;       // first row of this pass inside the image tile
+    const long long n0 = rt * TILE_M + r_base;
+    const int rows = (int)max(0LL, min((long long)sub_rows, z.N - n0));
     __syncthreads();
-    load_rows(z, n0, rows, D, tid, 256, [&](int r, int k, float v) { tile[r * LD + k] = v; });
+    if (rows > 0) load_rows(z, n0, rows, D, tid, 256, [&](int r, int k, float v) { tile[r * LD + k] = v; });
     __syncthreads();
+    if (tid < sub_rows) {                                  // exact fp32 |x|^2 per row (feeds the error bound)
+      float acc = 0.f;
+      if (tid < rows) for (int k = 0; k < D; ++k) { const float v = tile[tid * LD + ((k + tid) % D)]; acc = fmaf(v, v, acc); }
+      xnorm2[n0 + tid] = acc;
+    }
     // one thread per (row, 8-dim chunk)
     const int chunks = D >> 3;
-    for (int i = tid; i < TILE_M * chunks; i += 256) {
-      const int r = i / chunks, c = i - r * chunks;       // chunk c covers dims 8c..8c+7
+    for (int i = tid; i < sub_rows * chunks; i += 256) {
+      const int rl = i / chunks, c = i - rl * chunks;     // chunk c covers dims 8c..8c+7
+      const int r = r_base + rl;                          // row inside the 128-row image tile
       uint32_t hw[4], lw[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float a = (r < rows) ? tile[r * LD + 8 * c + 2 * e] : 0.f;
-        const float b = (r < rows) ? tile[r * LD + 8 * c + 2 * e + 1] : 0.f;
+        const float a = (rl < rows) ? tile[rl * LD + 8 * c + 2 * e] : 0.f;
+        const float b = (rl < rows) ? tile[rl * LD + 8 * c + 2 * e + 1] : 0.f;
         hw[e] = pack_bf16x2(a, b);
         lw[e] = pack_bf16x2(a - __uint_as_float(hw[e] << 16), b - __uint_as_float(hw[e] & 0xFFFF0000u));
       }
@@ -69,6 +80,7 @@ struct Params {
   const unsigned char* image;     // codebook tile image
   const float* neg_half_ee;
   const float* info;
+  const float* xnorm2;            // |x_n|^2 per row (padded to whole tiles)
   int K, NT, D;
   long long N, ntiles;            // rows, 128-row tiles
   int32_t* idx;
@@ -77,12 +89,13 @@ struct Params {
   int* err;
 };
 
-template <int KB, int NST, bool EPI8>
+template <int KB, int NST, bool EPI8, bool STREAM_A>
 __global__ void __launch_bounds__(NTHREADS, 1)
 vq_assign_tc_gen_kernel(const Params p) {
-  constexpr int SMEM_B = NST * IMG_TILE_BYTES;
+  constexpr int STAGE_BYTES = IMG_TILE_BYTES + (STREAM_A ? A_BLOCK : 0);   // [A block (streamed) |] codebook tile
+  constexpr int SMEM_B = NST * STAGE_BYTES;
   extern __shared__ __align__(1024) unsigned char smem[];
-  constexpr int SMEM_A = KB * A_BLOCK;
+  constexpr int SMEM_A = STREAM_A ? 0 : KB * A_BLOCK;
   unsigned char* sA = smem;                       // [KB][hi 16K | lo 16K]
   unsigned char* sB = smem + SMEM_A;              // [NST][32768]
   float* sN = reinterpret_cast<float*>(sB + SMEM_B);
@@ -117,16 +130,21 @@ vq_assign_tc_gen_kernel(const Params p) {
     if (lane == 0) {
       unsigned it = 0, nt = 0, tile_i = 0;
       for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_i) {
-        mbar_wait(smem_u32(aempty), (tile_i & 1) ^ 1, p.err, 7);             // MMAs of the previous tile left A
-        mbar_expect_tx(smem_u32(afull), SMEM_A);
-        bulk_g2s(smem_u32(sA), p.zimg + (size_t)tile * SMEM_A, SMEM_A, smem_u32(afull));
+        if (!STREAM_A) {
+          mbar_wait(smem_u32(aempty), (tile_i & 1) ^ 1, p.err, 7);           // MMAs of the previous tile left A
+          mbar_expect_tx(smem_u32(afull), SMEM_A);
+          bulk_g2s(smem_u32(sA), p.zimg + (size_t)tile * (KB * A_BLOCK), SMEM_A, smem_u32(afull));
+        }
         for (int j = 0; j < NT; ++j, ++nt) {
           for (int kb = 0; kb < KB; ++kb, ++it) {
             const unsigned s = it % NST, ph = (it / NST) & 1;
             mbar_wait(smem_u32(empty + s), ph ^ 1, p.err, 1);
-            mbar_expect_tx(smem_u32(full + s), IMG_TILE_BYTES);
-            bulk_g2s(smem_u32(sB + (size_t)s * IMG_TILE_BYTES), p.image + ((size_t)j * KB + kb) * IMG_TILE_BYTES,
-                     IMG_TILE_BYTES, smem_u32(full + s));
+            mbar_expect_tx(smem_u32(full + s), STAGE_BYTES);
+            if (STREAM_A)
+              bulk_g2s(smem_u32(sB + (size_t)s * STAGE_BYTES), p.zimg + ((size_t)tile * KB + kb) * A_BLOCK, A_BLOCK,
+                       smem_u32(full + s));
+            bulk_g2s(smem_u32(sB + (size_t)s * STAGE_BYTES + (STREAM_A ? A_BLOCK : 0)),
+                     p.image + ((size_t)j * KB + kb) * IMG_TILE_BYTES, IMG_TILE_BYTES, smem_u32(full + s));
             if (kb == 0) {          // slot nt % NHS is free: see the reuse-distance argument in assign_tc.cu
               mbar_expect_tx(smem_u32(nhfull + nt % NHS), BN * 4);
               bulk_g2s(smem_u32(sN + (size_t)(nt % NHS) * BN), p.neg_half_ee + (size_t)j * BN, BN * 4,
@@ -140,7 +158,7 @@ vq_assign_tc_gen_kernel(const Params p) {
     if (lane == 0) {
       unsigned it = 0, nt = 0, tile_i = 0;
       for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_i) {
-        mbar_wait(smem_u32(afull), tile_i & 1, p.err, 3);
+        if (!STREAM_A) mbar_wait(smem_u32(afull), tile_i & 1, p.err, 3);
         for (int j = 0; j < NT; ++j, ++nt) {
           const unsigned as = nt & 1;
           const uint32_t d_tmem = tmem_base + as * BN;
@@ -149,8 +167,9 @@ vq_assign_tc_gen_kernel(const Params p) {
             mbar_wait(smem_u32(full + s), (it / NST) & 1, p.err, 2);
             if (kb == 0) mbar_wait(smem_u32(tempty + as), ((nt >> 1) & 1) ^ 1, p.err, 4);
             tc_fence_after();
-            const uint32_t a_hi = smem_u32(sA + (size_t)kb * A_BLOCK), a_lo = a_hi + TILE_M * 128;
-            const uint32_t b_hi = smem_u32(sB + (size_t)s * IMG_TILE_BYTES), b_lo = b_hi + IMG_HALF_BYTES;
+            const uint32_t a_hi = STREAM_A ? smem_u32(sB + (size_t)s * STAGE_BYTES) : smem_u32(sA + (size_t)kb * A_BLOCK);
+            const uint32_t a_lo = a_hi + TILE_M * 128;
+            const uint32_t b_hi = smem_u32(sB + (size_t)s * STAGE_BYTES + (STREAM_A ? A_BLOCK : 0)), b_lo = b_hi + IMG_HALF_BYTES;
 #pragma unroll
             for (int sp = 0; sp < 3; ++sp) {            // x_hi.E_hi + x_lo.E_hi + x_hi.E_lo
               const uint32_t a = (sp == 1) ? a_lo : a_hi;
@@ -162,7 +181,7 @@ vq_assign_tc_gen_kernel(const Params p) {
             umma_commit(smem_u32(empty + s));
           }
           umma_commit(smem_u32(tfull + as));
-          if (j == NT - 1) umma_commit(smem_u32(aempty));
+          if (!STREAM_A && j == NT - 1) umma_commit(smem_u32(aempty));
         }
       }
     }
@@ -179,24 +198,7 @@ vq_assign_tc_gen_kernel(const Params p) {
     for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_i) {
       const long long n0 = tile * TILE_M;
       const int rows = (int)min((long long)TILE_M, p.N - n0);
-      mbar_wait(smem_u32(afull), tile_i & 1, p.err, 10);
-      float xx = 0.f;
-      for (int kb = 0; kb < KB; ++kb) {
-        const unsigned char* a_hi = sA + (size_t)kb * A_BLOCK;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int off = row * 128 + ((j ^ (row & 7)) << 4);
-          const uint4 h = *reinterpret_cast<const uint4*>(a_hi + off);
-          const uint4 l = *reinterpret_cast<const uint4*>(a_hi + TILE_M * 128 + off);
-          const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float v0 = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
-            const float v1 = __uint_as_float(hw[e] & 0xFFFF0000u) + __uint_as_float(lw[e] & 0xFFFF0000u);
-            xx = fmaf(v0, v0, xx); xx = fmaf(v1, v1, xx);
-          }
-        }
-      }
+      const float xx = __ldg(p.xnorm2 + n0 + row);         // exact fp32 |x|^2 from z_image_kernel
       float g1 = -INFINITY, g2 = -INFINITY; int gi = 0;
       for (int j = 0; j < NT; ++j, ++nt) {
         const unsigned as = nt & 1;
@@ -257,17 +259,18 @@ vq_assign_tc_gen_kernel(const Params p) {
   if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
-template <int KB, int NST, bool EPI8>
+template <int KB, int NST, bool EPI8, bool STREAM_A>
 static int launch_kb(const Params& p, cudaStream_t stream) {
-  constexpr int smem = KB * A_BLOCK + NST * IMG_TILE_BYTES + SMEM_NH + SMEM_BAR + (EPI8 ? SMEM_XCH : 0);
+  constexpr int smem = (STREAM_A ? 0 : KB * A_BLOCK) + NST * (IMG_TILE_BYTES + (STREAM_A ? A_BLOCK : 0)) + SMEM_NH + SMEM_BAR +
+                       (EPI8 ? SMEM_XCH : 0);
   static_assert(smem <= 232448, "shared memory budget");
   static thread_local bool configured = false;
   if (!configured) {
-    VQ_CUDA(cudaFuncSetAttribute(vq_assign_tc_gen_kernel<KB, NST, EPI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VQ_CUDA(cudaFuncSetAttribute(vq_assign_tc_gen_kernel<KB, NST, EPI8, STREAM_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const int grid = (int)max(1LL, min(p.ntiles, (long long)sm_count()));
-  vq_assign_tc_gen_kernel<KB, NST, EPI8><<<grid, NTHREADS, smem, stream>>>(p);
+  vq_assign_tc_gen_kernel<KB, NST, EPI8, STREAM_A><<<grid, NTHREADS, smem, stream>>>(p);
   VQ_LAUNCH_CHECK("vq_assign_tc_gen_kernel");
   return VQB200_OK;
 }
@@ -275,14 +278,14 @@ static int launch_kb(const Params& p, cudaStream_t stream) {
 }  // namespace tcg
 
 bool assign_tc_gen_eligible(const ZView& z, int K, int D) {
-  return (D == 128 || D == 256) && z.C == D && K >= 1 && z.N >= 1;
+  return (D == 128 || D == 256 || D == 512) && z.C == D && K >= 1 && z.N >= 1;
 }
 
 // workspace: 256 B header (list_count, err) + row list (N int32, padded) + split-bf16 row image
 static size_t gen_list_bytes(long long N) { return ((size_t)N * sizeof(int32_t) + 1023) & ~(size_t)1023; }
 size_t assign_tc_gen_workspace_bytes(long long N, int D) {
   const long long tiles = (N + tcc::TILE_M - 1) / tcc::TILE_M;
-  return 1024 + gen_list_bytes(N) + (size_t)tiles * (D / 64) * tcg::A_BLOCK + 1024;
+  return 1024 + gen_list_bytes(N) + (size_t)tiles * tcc::TILE_M * sizeof(float) + (size_t)tiles * (D / 64) * tcg::A_BLOCK + 1024;
 }
 
 int launch_assign_tc_gen(const ZView& z, const float* E, const float* ee, const void* image, const float* info,
@@ -297,7 +300,10 @@ int launch_assign_tc_gen(const ZView& z, const float* E, const float* ee, const 
   VQ_CUDA(cudaMemsetAsync(hdr, 0, 256, stream));
   const int KB = D / 64;
   Params p;
-  p.zimg = base + 1024 + gen_list_bytes(z.N);
+  const long long tiles = (z.N + TILE_M - 1) / TILE_M;
+  float* xn = reinterpret_cast<float*>(base + 1024 + gen_list_bytes(z.N));
+  p.xnorm2 = xn;
+  p.zimg = base + 1024 + gen_list_bytes(z.N) + (size_t)tiles * TILE_M * sizeof(float);     // stays 1024-byte aligned
   p.image = reinterpret_cast<const unsigned char*>(image);
   p.neg_half_ee = reinterpret_cast<const float*>(p.image + img_tiles_bytes(K, D));
   p.info = info;
@@ -311,18 +317,23 @@ int launch_assign_tc_gen(const ZView& z, const float* E, const float* ee, const 
   p.err = hdr + 1;
   // 1. split the input into the bf16 row image
   {
-    const size_t smem = (size_t)TILE_M * (D + 4) * sizeof(float);
+    const int sub_rows = (D <= 256) ? TILE_M : TILE_M / 2;          // D = 512: two 64-row passes per image tile
+    const size_t smem = (size_t)sub_rows * (D + 4) * sizeof(float);
     static thread_local size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
       VQ_CUDA(cudaFuncSetAttribute(z_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
     }
-    const int grid = (int)max(1LL, min(p.ntiles, (long long)sm_count() * (smem > 100 * 1024 ? 1 : 2)));
-    z_image_kernel<<<grid, 256, smem, stream>>>(z, D, KB, const_cast<unsigned char*>(p.zimg), p.ntiles);
+    const long long work = p.ntiles * (TILE_M / sub_rows);
+    const int grid = (int)max(1LL, min(work, (long long)sm_count() * (smem > 100 * 1024 ? 1 : 2)));
+    z_image_kernel<<<grid, 256, smem, stream>>>(z, D, KB, sub_rows, const_cast<unsigned char*>(p.zimg), xn, p.ntiles);
     VQ_LAUNCH_CHECK("z_image_kernel");
   }
   // 2. tcgen05 filter
-  int rc = (KB == 2) ? launch_kb<2, 4, true>(p, stream) : launch_kb<4, 3, false>(p, stream);   // ring depth = what 227 KiB allows
+  // ring depth / epilogue width = what 227 KiB of shared memory allow
+  int rc = (KB == 2) ? launch_kb<2, 4, true, false>(p, stream)
+         : (KB == 4) ? launch_kb<4, 3, false, false>(p, stream)
+                     : launch_kb<8, 3, false, true>(p, stream);
   if (rc != VQB200_OK) return rc;
   // 3. exact re-do of the rows the filter could not prove
   return launch_assign_simt(z, E, ee, K, D, idx, best, p.list, p.list_count, z.N, stream);

@@ -367,7 +367,7 @@ def test_cfg3_rvq_chunk():
         print("cfg3 chunk step", step, "benign flips", flips)
 
 
-@pytest.mark.parametrize("K,D", [(512, 64), (2048, 128), (4096, 64), (1000, 24), (16384, 256)])
+@pytest.mark.parametrize("K,D", [(512, 64), (2048, 128), (4096, 64), (1000, 24), (16384, 256), (1024, 512)])
 def test_cfg5_points(K, D):
     """cfg5 sweep points on a 16 384-vector chunk (the oracle materialises N x K)."""
     vq = _mods()

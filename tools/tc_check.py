@@ -79,4 +79,7 @@ if __name__ == "__main__":
     total += case(1000000, 1, 4096, "normal", D=128, time_it=True, perm=True)
     total += case(500000, 1, 4096, "normal", D=256, time_it=True, perm=True)
     total += case(100000, 10, 2048, "small", D=256, time_it=True)
+    total += case(700, 3, 300, "small", D=512)
+    total += case(3686, 1, 1024, "degenerate", D=512, perm=True)
+    total += case(262144, 1, 4096, "normal", D=512, time_it=True, perm=True)
     print("TOTAL MISMATCHES", total)
