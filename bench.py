@@ -36,7 +36,6 @@ WORKLOADS = {
     # name: (kind, S, K, D, windows B, T)
     "cfg3_rvq4_k1024_d64": dict(kind="rvq", S=4, K=1024, D=64, B=1_000_000, T=10),
     "cfg1_ema_k1024_d64": dict(kind="vq", S=1, K=1024, D=64, B=4096, T=10),
-    "cfg5_ema_k4096_d128": dict(kind="vq", S=1, K=4096, D=128, B=4_194_304, T=1),
 }
 HEADLINE = "cfg3_rvq4_k1024_d64"
 

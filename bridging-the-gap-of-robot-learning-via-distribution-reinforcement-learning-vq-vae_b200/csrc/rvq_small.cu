@@ -10,7 +10,6 @@
 // (d = fl(fl(|x|^2 + |E|^2) - 2 x.E), first minimum, NaN wins) and of ema.cu / gather.cu.
 // Eligible: D == 64, N <= 4096, K <= 4096, S <= 8, single process (no inter-GPU all-reduce inside the launch).
 #include <cooperative_groups.h>
-#include <stdlib.h>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -45,7 +44,6 @@ struct Args {
   int32_t* idx;                                 // [S][N]
   float* out;                                   // [B,C,T] contiguous
   float* m3;                                    // [S][3] loss, perplexity, dcr
-  long long* dbg;                               // phase timestamps (development)
 };
 
 __device__ __forceinline__ long long stats_offset(const Args& a, int s) {
@@ -79,9 +77,6 @@ rvq_small_kernel(const Args a) {
   const long long row0 = (long long)rank * rows_per;
   const int rows = (int)max(0LL, min((long long)rows_per, N - row0));
   const int C = (int)a.z.C, T = (int)a.z.T;
-  int dbg_i = 0;
-#define STAMP() do { if (a.dbg && rank == 0 && tid == 0 && dbg_i < 60) a.dbg[dbg_i++] = clock64(); } while (0)
-  STAMP();
 
   // ---- load this CTA's rows, zero the statistics of all stages ----
   for (int i = tid; i < rows * D; i += NT) {
@@ -94,7 +89,6 @@ rvq_small_kernel(const Args a) {
     if (rank == 0 && tid < a.S) a.sse[tid] = 0.0;
   }
   cluster.sync();
-  STAMP();
 
   for (int s = 0; s < a.S; ++s) {
     const int K = a.K[s];
@@ -123,7 +117,6 @@ rvq_small_kernel(const Args a) {
         for (int k0 = 0; k0 < K; k0 += CHUNK) {
           const int kc = min(CHUNK, K - k0);
           __syncthreads();                                              // previous chunk fully consumed
-          if (s == 0) STAMP();
           {
             // CHUNK*D/4 = 2048 float4 = 8 per thread: issue all loads before the first store (one L2 round trip)
             const float4* src = reinterpret_cast<const float4*>(E + (size_t)k0 * D);
@@ -136,7 +129,6 @@ rvq_small_kernel(const Args a) {
             for (int u = 0; u < 8; ++u) { const int i = tid + u * NT; if (i < n4) dst[i] = t[u]; }
           }
           __syncthreads();
-          if (s == 0) STAMP();
           if (pass == 0) {
             // |E_k|^2 of the chunk (needed once per stage): one code per thread, 16-byte reads rotated by the
             // lane id so that the 32 rows a warp touches hit different banks
@@ -151,7 +143,6 @@ rvq_small_kernel(const Args a) {
               ee[k0 + tid] = acc;
             }
             __syncthreads();
-            if (s == 0) STAMP();
           }
           if (blk < nb) {
             // four codes per iteration: four independent FMA chains (each still sums dims 0..63 in order)
@@ -196,7 +187,6 @@ rvq_small_kernel(const Args a) {
       }
     }
 
-    STAMP();
     // ---- K3a: statistics (counts always: they feed perplexity / dcr) ----
     for (int r = tid; r < rows; r += NT) atomicAdd(cnt + rowk[r], 1.0f);
     if (a.training_ema) {
@@ -209,7 +199,6 @@ rvq_small_kernel(const Args a) {
     if (a.training_ema) {
       __threadfence();
       cluster.sync();                                      // every CTA's statistics are in
-      STAMP();
       // ---- K3b step 1 (cluster rank 0): cs <- decay*cs + (1-decay)*cnt ; n ; normalised cluster sizes ----
       if (rank == 0) {
         float* cs = a.cs[s];
@@ -234,7 +223,6 @@ rvq_small_kernel(const Args a) {
         __threadfence();
       }
       cluster.sync();
-      STAMP();
       // ---- K3b step 2 (all CTAs, code slices): w <- decay*w + (1-decay)*dw ; E <- w / cluster ----
       {
         float* wv = a.w[s];
@@ -264,7 +252,6 @@ rvq_small_kernel(const Args a) {
         __threadfence();
       }
       cluster.sync();                                      // the updated codebook is complete
-      STAMP();
     }
 
     // ---- K2: gather (post-update codebook), straight-through value, loss sum, running sum, next residual ----
@@ -310,7 +297,6 @@ rvq_small_kernel(const Args a) {
       }
     }
     __syncthreads();
-    STAMP();
   }
 
   // ---- loss / perplexity / dcr of every stage (cluster rank 0, one warp per stage) ----
@@ -344,7 +330,6 @@ rvq_small_kernel(const Args a) {
     }
   }
   __syncthreads();
-  STAMP();
 }
 
 }  // namespace small
@@ -363,7 +348,7 @@ int vqb200_rvq_small_eligible(int64_t N, int64_t D, int32_t S, const int64_t* K)
 size_t vqb200_rvq_small_workspace_floats(int32_t S, const int64_t* K) {
   size_t n = 0;
   for (int s = 0; s < S; ++s) n += (size_t)K[s] * (small::D + 1) + (size_t)K[s] + 8;
-  return n + 16 + 256;
+  return n + 16;
 }
 
 int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,
@@ -398,10 +383,6 @@ int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, in
   a.stats = workspace;
   a.scratch = workspace + ((stats_floats + 3) & ~(size_t)3);
   a.sse = sse; a.idx = idx; a.out = out; a.m3 = m3;
-  {
-    size_t sc = 0; for (int s = 0; s < S; ++s) sc += (size_t)K[s] + 8;
-    a.dbg = getenv("VQB200_SMALL_DEBUG") ? reinterpret_cast<long long*>(a.scratch + ((sc + 3) & ~(size_t)3) + 4) : nullptr;
-  }
 
   const size_t smem = ((size_t)MAX_ROWS_PER_CTA * LDR + MAX_K + 8 * 32 + (size_t)CHUNK * D) * sizeof(float) +
                       (8 * 32 + MAX_ROWS_PER_CTA) * sizeof(int);

@@ -6,6 +6,7 @@ names; the nn.Modules in quantizers.py adapt them to the reference's real 3-tupl
 """
 from __future__ import annotations
 
+import ctypes
 from ctypes import c_double, c_float, c_int, c_int64, c_size_t
 from typing import List, Optional, Sequence, Tuple
 
@@ -155,7 +156,6 @@ class _RVQFn(torch.autograd.Function):
         ema_train = cfg.training and cfg.use_ema
         world = _dist.world_size() if ema_train else 1
         e0_snapshot = None
-        import ctypes
         Ks = (ctypes.c_int64 * S)(*[weights[s].shape[0] for s in range(S)])
         for s in range(S):
             if weights[s].shape[1] != C:

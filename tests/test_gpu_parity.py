@@ -393,14 +393,13 @@ def test_strided_views_agree():
     base = torch.randn(B, D, Tt, device=DEV)
     _, q0, _ = mod(base)
     i0 = mod.last_indices.clone()
-    views = {
-        "btc_permuted": base.permute(0, 2, 1).contiguous().permute(0, 2, 1),
-        "padded": torch.randn(B, D + 3, Tt + 5, device=DEV)[:, :D, :Tt].copy_(base),
-        "expanded_b": base[:, :, :].clone(),
-    }
     big = torch.zeros(B, D + 3, Tt + 5, device=DEV)
     big[:, :D, :Tt] = base
-    views["padded"] = big[:, :D, :Tt]
+    views = {
+        "btc_permuted": base.permute(0, 2, 1).contiguous().permute(0, 2, 1),     # [B,T,C] memory, strides (T*C, 1, C)
+        "padded": big[:, :D, :Tt],                                               # arbitrary strides
+        "clone": base.clone(),
+    }
     for name, v in views.items():
         assert torch.equal(v, base)
         _, q, _ = mod(v)
