@@ -141,8 +141,9 @@ gather_bulk_kernel(const float* __restrict__ z, const float* __restrict__ E, con
                    double* __restrict__ sse) {
   using namespace ptx;
   extern __shared__ __align__(128) float smem[];
+  constexpr int STAGES = TWO ? 2 : BULK_STAGES;         // 64 KiB (TWO) / 48 KiB per CTA: 3 / 4 CTAs per SM
   constexpr int STAGE_FLOATS = (TWO ? 2 : 1) * TILE_ELEMS;
-  __shared__ uint64_t full[BULK_STAGES];
+  __shared__ uint64_t full[STAGES];
   __shared__ int s_off[256];
   __shared__ int s_code[2][256];
   const int tid = threadIdx.x;
@@ -151,7 +152,7 @@ gather_bulk_kernel(const float* __restrict__ z, const float* __restrict__ E, con
   const bool y_in = TWO && ((mode == GM_RVQ && accum_init) || mode == GM_BACKWARD);
   const float* ysrc = (mode == GM_BACKWARD) ? in2 : o2;
   if (tid == 0) {
-    for (int s = 0; s < BULK_STAGES; ++s) mbar_init(smem_u32(full + s), 1);
+    for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(full + s), 1);
     fence_barrier_init();
   }
   if (tid < g.rows_per_tile) { const int b = tid / T, t = tid - b * T; s_off[tid] = b * D * T + t; }
@@ -163,7 +164,7 @@ gather_bulk_kernel(const float* __restrict__ z, const float* __restrict__ E, con
     return (int)min((long long)g.rows_per_tile, g.N - r0);
   };
   auto issue_load = [&](long long i) {           // thread 0 only
-    const int s = (int)(i % BULK_STAGES);
+    const int s = (int)(i % STAGES);
     const long long r0 = (blockIdx.x + i * gridDim.x) * g.rows_per_tile;
     const uint32_t bytes = (uint32_t)tile_rows(i) * D * 4;
     float* X = smem + (size_t)s * STAGE_FLOATS;
@@ -171,14 +172,14 @@ gather_bulk_kernel(const float* __restrict__ z, const float* __restrict__ E, con
     bulk_g2s(smem_u32(X), z + r0 * D, bytes, smem_u32(full + s));
     if (y_in) bulk_g2s(smem_u32(X + TILE_ELEMS), ysrc + r0 * D, bytes, smem_u32(full + s));
   };
-  if (tid == 0) for (long long i = 0; i < my_tiles && i < BULK_STAGES - 1; ++i) issue_load(i);
+  if (tid == 0) for (long long i = 0; i < my_tiles && i < STAGES - 1; ++i) issue_load(i);
   if (my_tiles > 0 && tid < tile_rows(0)) {
     const int k = __ldg(idx + (long long)blockIdx.x * g.rows_per_tile + tid);
     s_code[0][tid] = min(max(k, 0), K - 1);
   }
   float part = 0.f;
   for (long long i = 0; i < my_tiles; ++i) {
-    const int s = (int)(i % BULK_STAGES);
+    const int s = (int)(i % STAGES);
     const long long r0 = (blockIdx.x + i * gridDim.x) * g.rows_per_tile;
     const int rows = tile_rows(i);
     const int n = rows * D;
@@ -188,12 +189,12 @@ gather_bulk_kernel(const float* __restrict__ z, const float* __restrict__ E, con
     int next_code = 0;
     const bool have_next = (i + 1 < my_tiles) && tid < tile_rows(i + 1);
     if (have_next) next_code = __ldg(idx + (blockIdx.x + (i + 1) * gridDim.x) * (long long)g.rows_per_tile + tid);
-    if (tid == 0 && i + BULK_STAGES - 1 < my_tiles) {
+    if (tid == 0 && i + STAGES - 1 < my_tiles) {
       bulk_wait_read<0>();                       // the store that last read stage (i-1)%STAGES has drained it
-      issue_load(i + BULK_STAGES - 1);
+      issue_load(i + STAGES - 1);
     }
     __syncthreads();                             // s_code[i&1] written (previous iteration / prologue)
-    mbar_wait(smem_u32(full + s), (uint32_t)((i / BULK_STAGES) & 1), nullptr, 0);
+    mbar_wait(smem_u32(full + s), (uint32_t)((i / STAGES) & 1), nullptr, 0);
     const int* code = s_code[i & 1];
     // one thread = 4 consecutive dims of one row (16-byte codeword loads), U row-quads in flight per thread
     constexpr int U = 4;
@@ -456,17 +457,17 @@ int try_gather_tile(const ZView& z, const float* E, const int32_t* idx, int K, i
   const bool two = (mode == GM_RVQ && o2) || (mode == GM_BACKWARD && in2);
   static const bool use_bulk = !(getenv("VQB200_NO_BULK") && atoi(getenv("VQB200_NO_BULK")));
   if (use_bulk && (g.rows_per_tile * g.D * 4) % 16 == 0) {
-    const size_t smem = (size_t)BULK_STAGES * (two ? 2 : 1) * TILE_ELEMS * sizeof(float);
+    const size_t smem = (size_t)(two ? 2 : BULK_STAGES) * (two ? 2 : 1) * TILE_ELEMS * sizeof(float);
     static thread_local bool configured = false;
     if (!configured) {
       cudaError_t e1 = cudaFuncSetAttribute(gather_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            BULK_STAGES * 2 * TILE_ELEMS * (int)sizeof(float));
+                                            2 * 2 * TILE_ELEMS * (int)sizeof(float));
       cudaError_t e2 = cudaFuncSetAttribute(gather_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             BULK_STAGES * TILE_ELEMS * (int)sizeof(float));
       if (e1 != cudaSuccess || e2 != cudaSuccess) return cuda_fail(e1 != cudaSuccess ? e1 : e2, "cudaFuncSetAttribute(gather_bulk_kernel)");
       configured = true;
     }
-    const int grid = tile_grid(g, two ? 2 : 4);
+    const int grid = tile_grid(g, two ? 3 : 4);
     if (two) gather_bulk_kernel<true><<<grid, TILE_NT, smem, stream>>>(z.p, E, idx, K, g, mode, o1, o2, in2, accum_init, g_loss, coef, sse);
     else gather_bulk_kernel<false><<<grid, TILE_NT, smem, stream>>>(z.p, E, idx, K, g, mode, o1, o2, in2, accum_init, g_loss, coef, sse);
     count_launch();
