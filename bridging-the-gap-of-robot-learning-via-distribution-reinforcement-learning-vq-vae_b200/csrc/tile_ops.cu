@@ -141,7 +141,7 @@ gather_bulk_kernel(const float* __restrict__ z, const float* __restrict__ E, con
                    double* __restrict__ sse) {
   using namespace ptx;
   extern __shared__ __align__(128) float smem[];
-  constexpr int STAGES = TWO ? 2 : BULK_STAGES;         // 64 KiB (TWO) / 48 KiB per CTA: 3 / 4 CTAs per SM
+  constexpr int STAGES = 2;                            // 64 KiB (TWO) / 32 KiB per CTA: 3 / 6 CTAs per SM
   constexpr int STAGE_FLOATS = (TWO ? 2 : 1) * TILE_ELEMS;
   __shared__ uint64_t full[STAGES];
   __shared__ int s_off[256];
@@ -267,6 +267,7 @@ gather_bulk_kernel(const float* __restrict__ z, const float* __restrict__ E, con
 // Same bulk-TMA tile pipeline as gather_bulk_kernel.
 // ------------------------------------------------------------------------------------------
 constexpr int CHAIN_MAX_S = 8;
+constexpr int CHAIN_STAGES = 2;
 struct ChainArgs {
   const float* E[CHAIN_MAX_S];
   const int32_t* idx[CHAIN_MAX_S];
@@ -280,13 +281,13 @@ __global__ void __launch_bounds__(TILE_NT)
 rvq_chain_kernel(const float* __restrict__ z, ChainArgs ca, TileGeom g, float* __restrict__ out) {
   using namespace ptx;
   extern __shared__ __align__(128) float smem[];
-  __shared__ uint64_t full[BULK_STAGES];
+  __shared__ uint64_t full[CHAIN_STAGES];
   __shared__ int s_off[256];
   __shared__ int s_code[2][CHAIN_MAX_S][64];         // rows_per_tile <= 64 for this kernel
   const int tid = threadIdx.x;
   const int D = g.D, T = g.T;
   if (tid == 0) {
-    for (int s = 0; s < BULK_STAGES; ++s) mbar_init(smem_u32(full + s), 1);
+    for (int s = 0; s < CHAIN_STAGES; ++s) mbar_init(smem_u32(full + s), 1);
     fence_barrier_init();
   }
   if (tid < g.rows_per_tile) { const int b = tid / T, t = tid - b * T; s_off[tid] = b * D * T + t; }
@@ -297,7 +298,7 @@ rvq_chain_kernel(const float* __restrict__ z, ChainArgs ca, TileGeom g, float* _
     return (int)min((long long)g.rows_per_tile, g.N - r0);
   };
   auto issue_load = [&](long long i) {
-    const int s = (int)(i % BULK_STAGES);
+    const int s = (int)(i % CHAIN_STAGES);
     const long long r0 = (blockIdx.x + i * gridDim.x) * g.rows_per_tile;
     const uint32_t bytes = (uint32_t)tile_rows(i) * D * 4;
     mbar_expect_tx(smem_u32(full + s), bytes);
@@ -312,24 +313,24 @@ rvq_chain_kernel(const float* __restrict__ z, ChainArgs ca, TileGeom g, float* _
       s_code[buf][s][r] = min(max(k, 0), ca.K[s] - 1);
     }
   };
-  if (tid == 0) for (long long i = 0; i < my_tiles && i < BULK_STAGES - 1; ++i) issue_load(i);
+  if (tid == 0) for (long long i = 0; i < my_tiles && i < CHAIN_STAGES - 1; ++i) issue_load(i);
   if (my_tiles > 0) load_codes(0, 0);
   float part[S];
 #pragma unroll
   for (int s = 0; s < S; ++s) part[s] = 0.f;
   for (long long i = 0; i < my_tiles; ++i) {
-    const int st = (int)(i % BULK_STAGES);
+    const int st = (int)(i % CHAIN_STAGES);
     const long long r0 = (blockIdx.x + i * gridDim.x) * g.rows_per_tile;
     const int rows = tile_rows(i);
     const int n = rows * D;
     float* X = smem + (size_t)st * TILE_ELEMS;
-    if (tid == 0 && i + BULK_STAGES - 1 < my_tiles) {
+    if (tid == 0 && i + CHAIN_STAGES - 1 < my_tiles) {
       bulk_wait_read<0>();
-      issue_load(i + BULK_STAGES - 1);
+      issue_load(i + CHAIN_STAGES - 1);
     }
     __syncthreads();                             // codes of this tile are in s_code[i & 1]
     if (i + 1 < my_tiles) load_codes(i + 1, (int)((i + 1) & 1));
-    mbar_wait(smem_u32(full + st), (uint32_t)((i / BULK_STAGES) & 1), nullptr, 0);
+    mbar_wait(smem_u32(full + st), (uint32_t)((i / CHAIN_STAGES) & 1), nullptr, 0);
     const int (*code)[64] = s_code[i & 1];
     // one thread = 4 consecutive dims of one row: codeword rows are fetched as 16-byte vectors (4x fewer
     // load instructions), U row-quads in flight per thread to cover the L2 latency of the S gathers
@@ -457,17 +458,17 @@ int try_gather_tile(const ZView& z, const float* E, const int32_t* idx, int K, i
   const bool two = (mode == GM_RVQ && o2) || (mode == GM_BACKWARD && in2);
   static const bool use_bulk = !(getenv("VQB200_NO_BULK") && atoi(getenv("VQB200_NO_BULK")));
   if (use_bulk && (g.rows_per_tile * g.D * 4) % 16 == 0) {
-    const size_t smem = (size_t)(two ? 2 : BULK_STAGES) * (two ? 2 : 1) * TILE_ELEMS * sizeof(float);
+    const size_t smem = (size_t)2 * (two ? 2 : 1) * TILE_ELEMS * sizeof(float);
     static thread_local bool configured = false;
     if (!configured) {
       cudaError_t e1 = cudaFuncSetAttribute(gather_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             2 * 2 * TILE_ELEMS * (int)sizeof(float));
       cudaError_t e2 = cudaFuncSetAttribute(gather_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            BULK_STAGES * TILE_ELEMS * (int)sizeof(float));
+                                            CHAIN_STAGES * TILE_ELEMS * (int)sizeof(float));
       if (e1 != cudaSuccess || e2 != cudaSuccess) return cuda_fail(e1 != cudaSuccess ? e1 : e2, "cudaFuncSetAttribute(gather_bulk_kernel)");
       configured = true;
     }
-    const int grid = tile_grid(g, two ? 3 : 4);
+    const int grid = tile_grid(g, two ? 3 : 6);
     if (two) gather_bulk_kernel<true><<<grid, TILE_NT, smem, stream>>>(z.p, E, idx, K, g, mode, o1, o2, in2, accum_init, g_loss, coef, sse);
     else gather_bulk_kernel<false><<<grid, TILE_NT, smem, stream>>>(z.p, E, idx, K, g, mode, o1, o2, in2, accum_init, g_loss, coef, sse);
     count_launch();
@@ -497,8 +498,8 @@ int try_rvq_chain(const ZView& z, int S, const float* const* E, const int32_t* c
     ca.E[s] = E[s]; ca.idx[s] = idx[s]; ca.K[s] = K[s]; ca.sse[s] = sse[s];
   }
   for (int s = S; s < CHAIN_MAX_S; ++s) { ca.E[s] = nullptr; ca.idx[s] = nullptr; ca.K[s] = 1; ca.sse[s] = nullptr; }
-  const size_t smem = (size_t)BULK_STAGES * TILE_ELEMS * sizeof(float);
-  const int grid = tile_grid(g, 4);
+  const size_t smem = (size_t)CHAIN_STAGES * TILE_ELEMS * sizeof(float);
+  const int grid = tile_grid(g, 6);
   auto launch = [&](auto kernel) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
