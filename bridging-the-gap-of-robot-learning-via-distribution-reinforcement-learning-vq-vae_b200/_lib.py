@@ -32,6 +32,8 @@ _SIGNATURES = {
     "vqb200_vq_histogram": (c_int, [_P, c_int64, c_int64, _P, _P]),
     "vqb200_vq_gather_st": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                     _P, _P, c_int64, _P, _P, _P, c_int, _P, _P]),
+    "vqb200_vq_assign_residual": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                          _P, _P, c_int64, _P, _P, _P, _P, _P, c_int64, _P, _P, c_size_t, c_int, _P]),
     "vqb200_rvq_output_chain": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                         ctypes.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "vqb200_rvq_small_eligible": (c_int, [c_int64, c_int64, ctypes.c_int32, _P]),

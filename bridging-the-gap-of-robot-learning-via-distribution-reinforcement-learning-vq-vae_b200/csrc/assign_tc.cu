@@ -69,6 +69,12 @@ struct Params {
   int32_t* list;                  // rows that need the exact kernel
   int32_t* list_count;
   int* err;
+  // fused residual update (RVQ stages >= 1): the staged rows are r_prev; the converter forms
+  // r = r_prev - st(r_prev, prev_E[prev_idx]) (models/vqvae.py:94-98), stores it to r_out and quantizes THAT
+  const int32_t* prev_idx;
+  const float* prev_E;
+  int prev_K;
+  float* r_out;                   // same layout as z (contiguous); null = plain assignment
   int dbg;                        // development knobs (VQB200_TC_DEBUG): 1 = skip epilogue math, 2 = one k-block
 };
 
@@ -211,6 +217,9 @@ vq_assign_tc_kernel(const Params p) {
         unsigned char* buf = sBuf + (size_t)(rt * 2 + pp) * BUF_BYTES;
         const float* raw = reinterpret_cast<const float*>(buf);
         float v[D];
+        const bool fuse = p.r_out != nullptr;       // staged modes only (checked by the launcher)
+        int kp = 0;                                 // previous stage's code of this row, fetched before the wait
+        if (fuse && row < rows) kp = min(max(__ldg(p.prev_idx + n0 + row), 0), p.prev_K - 1);
         if (staged && rows > 0) mbar_wait(smem_u32(rawfull + rt * 2 + pp), u & 1, p.err, 8);
         else mbar_wait(smem_u32(aempty + rt * 2 + pp), (u & 1) ^ 1, p.err, 5);     // nobody fills it for us: wait until free
         if (row < rows) {
@@ -233,11 +242,51 @@ vq_assign_tc_kernel(const Params p) {
 #pragma unroll
             for (int k = 0; k < D; ++k) v[k] = __ldg(src + (long long)k * p.z.sC);
           }
+          if (fuse) {                              // same three roundings as the stand-alone residual kernel
+            const float4* q4 = reinterpret_cast<const float4*>(p.prev_E + (size_t)kp * D);
+#pragma unroll
+            for (int c = 0; c < D / 4; ++c) {
+              const float4 q = __ldg(q4 + c);
+              const float qv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float x = v[4 * c + e];
+                v[4 * c + e] = __fsub_rn(x, __fadd_rn(x, __fsub_rn(qv[e], x)));
+              }
+            }
+          }
         } else {
 #pragma unroll
           for (int k = 0; k < D; ++k) v[k] = 0.f;
         }
         converter_sync();                          // every raw read of this buffer is done
+        if (fuse) {
+          // write the new residual back in the raw layout and stream the slab to r_out before converting in place
+          if (row < rows) {
+            float* rawW = reinterpret_cast<float*>(buf);
+            if (p.stage_mode == STG_ROWS) {
+              float4* dst = reinterpret_cast<float4*>(rawW + row * D);
+#pragma unroll
+              for (int c = 0; c < D / 4; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            } else {
+              const int T = (int)p.z.T;
+              const long long n = n0 + row;
+              const long long b = n / T; const int t = (int)(n - b * T);
+              float* dst = rawW + (b - n0 / T) * (D * T) + t;
+#pragma unroll
+              for (int k = 0; k < D; ++k) dst[k * T] = v[k];
+            }
+          }
+          fence_proxy_async();
+          converter_sync();
+          if (warp == 10 && lane == 0 && rows > 0) {
+            const StagePlan sp = stage_plan(p, n0, rows);
+            bulk_s2g(p.r_out + (sp.src - p.z.p), smem_u32(buf), sp.bytes);
+            bulk_commit();
+            bulk_wait_read<0>();                   // the store has read the buffer: safe to overwrite it
+          }
+          converter_sync();
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           uint32_t hw[4], lw[4];
@@ -345,9 +394,16 @@ bool assign_tc_eligible(const ZView& z, int K, int D) {
 // workspace: [0] int32 list_count, [1] int32 error word, [64 ..) int32 row list (N entries)
 size_t assign_tc_workspace_bytes(long long N) { return 256 + (size_t)(N > 0 ? N : 0) * sizeof(int32_t); }
 
+bool assign_tc_can_fuse_residual(const ZView& z, const float* r_out) {
+  const bool aligned = ((reinterpret_cast<uintptr_t>(z.p) | reinterpret_cast<uintptr_t>(r_out)) & 15) == 0;
+  if (!aligned || z.C != tc::D) return false;
+  if (z.mode == Z_ROW) return z.T == 1 && z.sB == tc::D;       // [N,64] rows == contiguous [N,64,1]
+  return z.mode == Z_BCT && z.T <= tcc::TILE_M;
+}
+
 int launch_assign_tc(const ZView& z, const float* E, const float* ee, const void* image, const float* info,
                      int K, int D, int32_t* idx, float* best, void* workspace, size_t workspace_bytes,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const int32_t* prev_idx, const float* prev_E, int prev_K, float* r_out) {
   using namespace tc;
   constexpr int TILE_M = tcc::TILE_M;
   VQ_CHECK_ARG(workspace_bytes >= assign_tc_workspace_bytes(z.N), VQB200_EWORKSPACE, "vq_assign(TC): workspace too small");
@@ -368,6 +424,7 @@ int launch_assign_tc(const ZView& z, const float* E, const float* ee, const void
   p.K = K;
   p.NT = (int)(img_kp(K) / IMG_TILE_CODES);
   p.idx = idx;
+  p.prev_idx = prev_idx; p.prev_E = prev_E; p.prev_K = prev_K; p.r_out = r_out;
   p.list = wsi + 64;
   p.list_count = wsi;
   p.err = wsi + 1;
@@ -389,6 +446,11 @@ int launch_assign_tc(const ZView& z, const float* E, const float* ee, const void
   vq_assign_tc_kernel<<<grid, NTHREADS, SMEM_TOTAL, stream>>>(p);
   VQ_LAUNCH_CHECK("vq_assign_tc_kernel");
   // exact re-do of the rows the filter could not prove (count lives on the device; no host sync)
+  if (r_out) {
+    VQ_CHECK_ARG(p.stage_mode != STG_DIRECT, VQB200_EUNSUPPORTED, "vq_assign(TC): fused residual needs a contiguous layout");
+    ZView zr = z; zr.p = r_out;                    // the rows that were quantized are the NEW residual
+    return launch_assign_simt(zr, E, ee, K, D, idx, best, p.list, p.list_count, z.N, stream);
+  }
   return launch_assign_simt(z, E, ee, K, D, idx, best, p.list, p.list_count, z.N, stream);
 }
 

@@ -51,7 +51,7 @@ gather_st_kernel(ZView z, const float* __restrict__ E, const int32_t* __restrict
   if (threadIdx.x < 32) {
     double v = threadIdx.x < 8 ? red[threadIdx.x] : 0.0;
     v = warp_sum(v);
-    if (threadIdx.x == 0 && v != 0.0) atomicAdd(sse, v);
+    if (threadIdx.x == 0 && sse && v != 0.0) atomicAdd(sse, v);
   }
 }
 
@@ -118,9 +118,9 @@ int vqb200_vq_gather_st(const float* z, int64_t B, int64_t C, int64_t T, int64_t
                         const float* E, const int32_t* idx, int64_t K, float* out, float* residual,
                         float* accum, int accum_init, double* sse, vqb200_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  VQ_CHECK_ARG(sse && ((z && E && idx) || B * C * T == 0), VQB200_EINVAL, "vq_gather_st: null pointer");
+  VQ_CHECK_ARG((z && E && idx) || B * C * T == 0, VQB200_EINVAL, "vq_gather_st: null pointer");
   VQ_CHECK_ARG(B >= 0 && C > 0 && T > 0 && K > 0 && C * T < (1LL << 31), VQB200_ESHAPE, "vq_gather_st: bad shape");
-  VQ_CUDA(cudaMemsetAsync(sse, 0, sizeof(double), stream));
+  if (sse) VQ_CUDA(cudaMemsetAsync(sse, 0, sizeof(double), stream));
   const long long total = B * C * T;
   if (total == 0) return VQB200_OK;
   const ZView zv = make_zview(z, B, C, T, sB, sC, sT);

@@ -201,11 +201,22 @@ class _RVQFn(torch.autograd.Function):
                 st.refresh(W)
                 r = residuals[s]
                 sB, sC, sT = r.stride()
-                if N > 0:
+                if N > 0 and s == 0:
                     ws = st.assign_workspace(N)
                     check(lib.vqb200_vq_assign(ptr(r), B, C, T, sB, sC, sT, ptr(W), ptr(st.ee), ptr(st.image),
                                                ptr(st.info), K, ptr(idx[s]), None, ptr(ws), c_size_t(ws.numel()),
                                                cfg.algo, stream), "vq_assign")
+                elif N > 0:
+                    # r_s = r_{s-1} - st_{s-1} (with the codebook stage s-1 has just updated) and its assignment in
+                    # one call: on the tensor-core path the residual update rides inside the assignment kernel
+                    ws = st.assign_workspace(N)
+                    rp = residuals[s - 1]
+                    pB, pC, pT = rp.stride()
+                    Wp = weights[s - 1].detach()
+                    check(lib.vqb200_vq_assign_residual(ptr(rp), B, C, T, pB, pC, pT, ptr(Wp), ptr(idx[s - 1]),
+                                                        Wp.shape[0], ptr(r), ptr(W), ptr(st.ee), ptr(st.image),
+                                                        ptr(st.info), K, ptr(idx[s]), ptr(ws), c_size_t(ws.numel()),
+                                                        cfg.algo, stream), "vq_assign_residual")
                 if ema_train:
                     check(lib.vqb200_ema_accumulate(ptr(r), B, C, T, sB, sC, sT, ptr(idx[s]), None, K,
                                                     ptr(st.stats), 0, stream), "ema_accumulate")
@@ -226,10 +237,6 @@ class _RVQFn(torch.autograd.Function):
                     check(lib.vqb200_vq_metrics(ptr(st.cnt), K, max(N * world, 1), ptr(st.sse), max(N * C, 1),
                                                 c_float(cfg.commitment_cost), 1 if cfg.use_ema else 0, ptr(m3[s]),
                                                 stream), "vq_metrics")
-                elif s < S - 1:
-                    # next residual r_{s+1} = r_s - st_s (the running sum is rebuilt once, after the last stage)
-                    check(lib.vqb200_vq_gather_st(ptr(r), B, C, T, sB, sC, sT, ptr(W), ptr(idx[s]), K, None,
-                                                  ptr(residuals[s + 1]), None, 0, ptr(st.sse), stream), "vq_gather_st")
             if not fused and not (cfg.plain and S == 1):
                 # all stages at once: out = ((0 + st_0) + st_1) + ... and the S loss sums, from z + indices + codebooks
                 Es = (ctypes.c_void_p * S)(*[weights[s].detach().data_ptr() for s in range(S)])

@@ -108,6 +108,19 @@ int vqb200_vq_gather_st(const float* z, int64_t B, int64_t C, int64_t T,
                         float* out, float* residual, float* accum, int accum_init,
                         double* sse, vqb200_stream_t stream);
 
+/* ---- K1 + residual update ------------------- models/vqvae.py:94-98 (r = r - q) then :30-38 --
+ * One call per RVQ stage s >= 1:  r_out = r_in - st  with  st = r_in + (E_prev[idx_prev] - r_in)  (bit-identical
+ * to the `residual` output of vqb200_vq_gather_st), then idx = argmin_k d(r_out, E_k) as vqb200_vq_assign.
+ * For D == 64 on a contiguous [B,C,T] tensor the update runs inside the tensor-core assignment kernel (the rows
+ * pass through shared memory anyway; saves one full read of r_in per stage); otherwise the two stand-alone
+ * kernels run back to back.  r_out: contiguous [B,C,T]. */
+int vqb200_vq_assign_residual(const float* r_in, int64_t B, int64_t C, int64_t T,
+                              int64_t sB, int64_t sC, int64_t sT,
+                              const float* E_prev, const int32_t* idx_prev, int64_t K_prev, float* r_out,
+                              const float* E, const float* ee, const void* image, const float* info, int64_t K,
+                              int32_t* idx, void* workspace, size_t workspace_bytes, int algo,
+                              vqb200_stream_t stream);
+
 /* ---- RVQ output chain ---------------------------------- models/vqvae.py:94-98, all stages at once --
  * Recomputes r_0 = z; st_s = r_s + (E_s[idx_s] - r_s); out = ((0 + st_0) + st_1) + ...; r_{s+1} = r_s - st_s
  * from z, the S index arrays and the S (already updated) codebooks -- bit-identical to running the stages one

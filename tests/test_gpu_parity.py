@@ -367,6 +367,50 @@ def test_cfg3_rvq_chunk():
         print("cfg3 chunk step", step, "benign flips", flips)
 
 
+@pytest.mark.parametrize("B,Tt,K,contig", [(4000, 10, 1024, True), (2311, 7, 300, True), (5003, 1, 512, True),
+                                            (3000, 10, 256, False), (100, 10, 64, True)])
+def test_assign_residual_entry_point(B, Tt, K, contig):
+    """vqb200_vq_assign_residual (residual update fused into the tensor-core assignment for contiguous D=64 input)
+    against the two stand-alone C-ABI calls and against the oracle's residual arithmetic (models/vqvae.py:94-98):
+    the residual must be bit-identical, the indices equal up to provably tied distances."""
+    import ctypes
+    vq = _mods()
+    from vqb200 import _lib
+    from vqb200._lib import ptr, stream_ptr, check
+    lib = _lib.load()
+    D = 64
+    rng = np.random.default_rng(B + K)
+    W0 = (0.3 * rng.standard_normal((K, D))).astype(np.float32)
+    W1 = (0.1 * rng.standard_normal((K, D))).astype(np.float32)
+    z_np = (0.5 * rng.standard_normal((B, D, Tt))).astype(np.float32)
+    z = T(z_np) if contig else T(np.ascontiguousarray(z_np.transpose(0, 2, 1))).transpose(1, 2)   # channel-last view
+    w0, w1 = T(W0), T(W1)
+    st0, st1 = vq.QuantizerState(K, D, torch.device(DEV)), vq.QuantizerState(K, D, torch.device(DEV))
+    idx0 = vq.vq_assign(z, w0, st0, _lib.ASSIGN_SIMT)
+    st1.refresh(w1)
+    ws = st1.assign_workspace(B * Tt)
+    r_ref, r_fused = torch.empty((B, D, Tt), device=DEV), torch.empty((B, D, Tt), device=DEV)
+    idx_fused = torch.empty((B, Tt), dtype=torch.int32, device=DEV)
+    sse = torch.zeros(1, dtype=torch.float64, device=DEV)
+    sB, sC, sT = z.stride()
+    s = stream_ptr(torch.device(DEV))
+    check(lib.vqb200_vq_gather_st(ptr(z), B, D, Tt, sB, sC, sT, ptr(w0), ptr(idx0), K, None, ptr(r_ref), None, 0,
+                                  ptr(sse), s), "gather_st")
+    idx_ref = vq.vq_assign(r_ref, w1, st1, _lib.ASSIGN_SIMT)
+    check(lib.vqb200_vq_assign_residual(ptr(z), B, D, Tt, sB, sC, sT, ptr(w0), ptr(idx0), K, ptr(r_fused), ptr(w1),
+                                        ptr(st1.ee), ptr(st1.image), ptr(st1.info), K, ptr(idx_fused), ptr(ws),
+                                        ctypes.c_size_t(ws.numel()), _lib.ASSIGN_AUTO, s), "assign_residual")
+    torch.cuda.synchronize()
+    assert torch.equal(r_fused, r_ref)
+    # oracle arithmetic: st = x + (q - x); r = x - st, all fp32
+    q = W0[N_(idx0).astype(np.int64)].transpose(0, 2, 1)
+    r_or = z_np - (z_np + (q - z_np))
+    assert np.array_equal(N_(r_fused), r_or)
+    d = vq_distances(np.ascontiguousarray(r_or.transpose(0, 2, 1)).reshape(-1, D), W1)
+    flips, bad, rows = check_indices(N_(idx_fused).reshape(-1).astype(np.int64), N_(idx_ref).reshape(-1).astype(np.int64), d)
+    assert bad == 0, f"{bad} non-benign flips of {flips} at rows {rows[:8]}"
+
+
 @pytest.mark.parametrize("K,D", [(512, 64), (2048, 128), (4096, 64), (1000, 24), (16384, 256), (1024, 512)])
 def test_cfg5_points(K, D):
     """cfg5 sweep points on a 16 384-vector chunk (the oracle materialises N x K)."""
