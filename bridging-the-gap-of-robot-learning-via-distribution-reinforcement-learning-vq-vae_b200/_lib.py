@@ -34,6 +34,14 @@ _SIGNATURES = {
                                     _P, _P, c_int64, _P, _P, _P, c_int, _P, _P]),
     "vqb200_vq_assign_residual": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                           _P, _P, c_int64, _P, _P, _P, _P, _P, c_int64, _P, _P, c_size_t, c_int, _P]),
+    "vqb200_proj_fused_eligible": (c_int, [c_int64, c_int64, c_int64, c_int64]),
+    "vqb200_proj_fused_grad_floats": (c_size_t, [c_int64, c_int64]),
+    "vqb200_fsq_fused_forward": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64,
+                                         _P, _P, _P, _P, _P, _P]),
+    "vqb200_lfq_fused_forward": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int64, c_float,
+                                         _P, _P, _P, _P, _P, _P]),
+    "vqb200_proj_fused_backward": (c_int, [c_int, _P, _P, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P, c_float,
+                                           _P, _P, _P]),
     "vqb200_rvq_output_chain": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                         ctypes.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "vqb200_rvq_small_eligible": (c_int, [c_int64, c_int64, ctypes.c_int32, _P]),

@@ -425,3 +425,82 @@ class _LFQFn(torch.autograd.Function):
 def lfq_sign(z_e: torch.Tensor, entropy_loss_weight: float = 0.1):
     """-> (z_q [B,d,T], loss, indices int64 [B,T], metrics = [loss, perplexity(#unique), dcr])."""
     return _LFQFn.apply(z_e, entropy_loss_weight)
+
+
+class _ProjFusedFn(torch.autograd.Function):
+    """Whole FSQ / LFQ module forward in one kernel (project_in -> round | sign -> project_out, indices, metrics,
+    LFQ entropy loss) and its autograd in one more (models/vqvae.py:126-154, :170-194)."""
+
+    @staticmethod
+    def forward(ctx, z, w_in, b_in, w_out, b_out, is_lfq, basis, codebook_size, weight):
+        lib = _lib.load()
+        B, D, T = z.shape
+        d = w_in.shape[0]
+        dev = z.device
+        out = torch.empty_like(z)
+        z_e = torch.empty((B, d, T), dtype=torch.float32, device=dev)
+        idx = torch.empty((B, T), dtype=torch.int64, device=dev)
+        m = torch.empty(3 if is_lfq else 2, dtype=torch.float32, device=dev)
+        wi, wo = w_in.detach().contiguous(), w_out.detach().contiguous()
+        bi, bo = b_in.detach().contiguous(), b_out.detach().contiguous()
+        with torch.cuda.device(dev):
+            if is_lfq:
+                check(lib.vqb200_lfq_fused_forward(ptr(z), B, D, T, ptr(wi), ptr(bi), ptr(wo), ptr(bo), d, c_float(weight),
+                                                   ptr(out), ptr(z_e), ptr(idx), ptr(_unique_workspace(dev)), ptr(m),
+                                                   stream_ptr(dev)), "lfq_fused_forward")
+            else:
+                check(lib.vqb200_fsq_fused_forward(ptr(z), B, D, T, ptr(wi), ptr(bi), ptr(wo), ptr(bo), d, ptr(basis),
+                                                   int(codebook_size), ptr(out), ptr(z_e), ptr(idx),
+                                                   ptr(_unique_workspace(dev)), ptr(m), stream_ptr(dev)), "fsq_fused_forward")
+        ctx.save_for_backward(z, z_e, wi, wo)
+        ctx.is_lfq, ctx.weight = bool(is_lfq), float(weight)
+        loss = m[0] if is_lfq else torch.zeros((), dtype=torch.float32, device=dev)
+        ctx.mark_non_differentiable(idx, m, z_e)
+        return out, loss, idx, m, z_e
+
+    @staticmethod
+    def backward(ctx, g_out, g_loss, *_):
+        lib = _lib.load()
+        z, z_e, wi, wo = ctx.saved_tensors
+        B, D, T = z.shape
+        d = wi.shape[0]
+        dev = z.device
+        g_out = torch.zeros_like(z) if g_out is None else _f32(g_out).contiguous()
+        if g_loss is not None:
+            g_loss = g_loss.to(torch.float32).contiguous()
+        elif ctx.is_lfq:
+            g_loss = torch.zeros((), dtype=torch.float32, device=dev)
+        g_z = torch.empty_like(z)
+        grads = torch.empty(int(lib.vqb200_proj_fused_grad_floats(D, d)), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.vqb200_proj_fused_backward(1 if ctx.is_lfq else 0, ptr(g_out), ptr(z), ptr(z_e), B, D, T, ptr(wi),
+                                                 ptr(wo), d, ptr(g_loss) if ctx.is_lfq else None, c_float(ctx.weight),
+                                                 ptr(g_z), ptr(grads), stream_ptr(dev)), "proj_fused_backward")
+        g_wi = grads[:d * D].view(d, D, 1)
+        g_bi = grads[d * D:d * D + d]
+        g_wo = grads[d * D + d:2 * d * D + d].view(D, d, 1)
+        g_bo = grads[2 * d * D + d:]
+        return g_z, g_wi, g_bi, g_wo, g_bo, None, None, None, None
+
+
+def proj_fused_eligible(z: torch.Tensor, d: int) -> bool:
+    """True when the one-pass kernels apply: contiguous fp32 [B,64,T] (T <= 64) on CUDA and d <= 16."""
+    if z.dim() != 3 or not z.is_cuda or z.dtype != torch.float32 or not z.is_contiguous() or z.shape[0] == 0:
+        return False
+    B, D, T = z.shape
+    return z.data_ptr() % 16 == 0 and bool(_lib.load().vqb200_proj_fused_eligible(B, D, int(d), T))
+
+
+def fsq_module_fused(z, project_in, project_out, basis, codebook_size):
+    """-> (out [B,D,T], indices int64 [B,T], metrics [perplexity(#unique), dcr], z_e [B,d,T])."""
+    if basis.dtype != torch.int32:
+        basis = basis.to(torch.int32)
+    out, _, idx, m2, z_e = _ProjFusedFn.apply(z, project_in.weight, project_in.bias, project_out.weight, project_out.bias,
+                                              False, basis.contiguous(), codebook_size, 0.0)
+    return out, idx, m2, z_e
+
+
+def lfq_module_fused(z, project_in, project_out, entropy_loss_weight):
+    """-> (out [B,D,T], loss, indices int64 [B,T], metrics [loss, perplexity(#unique), dcr], z_e [B,d,T])."""
+    return _ProjFusedFn.apply(z, project_in.weight, project_in.bias, project_out.weight, project_out.bias,
+                              True, None, 0, float(entropy_loss_weight))

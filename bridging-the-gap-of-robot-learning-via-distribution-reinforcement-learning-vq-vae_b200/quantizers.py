@@ -17,7 +17,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .functional import (QuantizerState, RVQConfig, rvq_quantize, fsq_round, lfq_sign)
+from .functional import (QuantizerState, RVQConfig, rvq_quantize, fsq_round, lfq_sign, proj_fused_eligible,
+                         fsq_module_fused, lfq_module_fused)
 
 
 def _require_cuda(z: torch.Tensor, who: str) -> torch.Tensor:
@@ -130,11 +131,21 @@ class FSQ(nn.Module):
         basis = torch.cumprod(torch.tensor([1] + list(levels[:-1]), dtype=torch.int64), dim=0)
         self.register_buffer("_basis", basis.to(torch.int32))
         self.codebook_size = math.prod(levels)
+        self.fuse_projections = True          # False: stock conv1d + the elementwise kernel (arbitrary layouts use it anyway)
         self.last_indices: Optional[torch.Tensor] = None
+        self.last_z_e: Optional[torch.Tensor] = None
 
     def forward(self, z):
         z = _require_cuda(z, "FSQ")
+        conv_ok = self.project_in.bias is not None and self.project_out.bias is not None
+        if self.fuse_projections and conv_ok and proj_fused_eligible(z, self.fsq_dim):
+            # one pass over z: both 1x1 projections ride inside the quantisation kernel
+            z_out, idx, m2, z_e = fsq_module_fused(z, self.project_in, self.project_out, self._basis, self.codebook_size)
+            self.last_indices, self.last_z_e = idx, z_e
+            loss = torch.zeros((), dtype=torch.float32, device=z.device)
+            return loss, z_out, {"perplexity": m2[0], "dcr": m2[1]}
         z_e = self.project_in(z)                                       # [B, d, T]
+        self.last_z_e = z_e.detach()
         z_hard, idx, m2 = fsq_round(z_e, self._basis, self.codebook_size)
         z_out = self.project_out(z_hard)
         self.last_indices = idx
@@ -154,11 +165,19 @@ class LFQ(nn.Module):
         self.project_in = nn.Conv1d(input_dim, codebook_dim, 1)
         self.project_out = nn.Conv1d(codebook_dim, input_dim, 1)
         self.register_buffer("_basis", 2 ** torch.arange(codebook_dim))
+        self.fuse_projections = True
         self.last_indices: Optional[torch.Tensor] = None
+        self.last_z_e: Optional[torch.Tensor] = None
 
     def forward(self, z):
         z = _require_cuda(z, "LFQ")
+        conv_ok = self.project_in.bias is not None and self.project_out.bias is not None
+        if self.fuse_projections and conv_ok and proj_fused_eligible(z, self.codebook_dim):
+            out, loss, idx, m3, z_e = lfq_module_fused(z, self.project_in, self.project_out, self.entropy_loss_weight)
+            self.last_indices, self.last_z_e = idx, z_e
+            return loss, out, {"perplexity": m3[1], "dcr": m3[2]}
         z_e = self.project_in(z)
+        self.last_z_e = z_e.detach()
         z_q, loss, idx, m3 = lfq_sign(z_e, self.entropy_loss_weight)
         out = self.project_out(z_q)
         self.last_indices = idx

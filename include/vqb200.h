@@ -193,6 +193,32 @@ int vqb200_lfq_forward(const float* z_e, int64_t B, int64_t d, int64_t T, float 
 int vqb200_lfq_backward(const float* z_e, const float* g_zq, const float* g_loss, int64_t numel,
                         float entropy_loss_weight, float* g_ze, vqb200_stream_t stream);
 
+/* ---- K5f: FSQ / LFQ with their 1x1 projections fused in ------------ SURVEY.md §8f rank 1 ----
+ * One pass over z [B,64,T] (contiguous, 16-byte aligned, T <= 64) for the whole module forward:
+ *   FSQ models/vqvae.py:126-154: z_e = W_in z + b_in; z_hard = z_e + (round(z_e) - z_e); idx, metrics as
+ *       vqb200_fsq_forward; out = W_out z_hard + b_out.
+ *   LFQ models/vqvae.py:170-194: same with the sign instead of the rounding and the entropy loss (out3[0]).
+ * W_in = project_in.weight [d,64,1], W_out = project_out.weight [64,d,1], d <= 16.  z_e [B,d,T] is written for the
+ * backward pass (and is what the index is bit-exact against).  vqb200_proj_fused_backward is the autograd of both:
+ *   g_z = W_in^T g_ze, g_ze = W_out^T g_out (+ LFQ entropy term, scaled by g_loss[0]);
+ *   grads = [dW_in (d*64) | db_in (d) | dW_out (64*d) | db_out (64)]  (zeroed inside the call). */
+int vqb200_proj_fused_eligible(int64_t B, int64_t D, int64_t d, int64_t T);
+size_t vqb200_proj_fused_grad_floats(int64_t D, int64_t d);
+int vqb200_fsq_fused_forward(const float* z, int64_t B, int64_t D, int64_t T,
+                             const float* W_in, const float* b_in, const float* W_out, const float* b_out,
+                             int64_t d, const int32_t* basis, int64_t codebook_size,
+                             float* out, float* z_e, int64_t* idx, void* workspace, float* out2,
+                             vqb200_stream_t stream);
+int vqb200_lfq_fused_forward(const float* z, int64_t B, int64_t D, int64_t T,
+                             const float* W_in, const float* b_in, const float* W_out, const float* b_out,
+                             int64_t d, float entropy_loss_weight,
+                             float* out, float* z_e, int64_t* idx, void* workspace, float* out3,
+                             vqb200_stream_t stream);
+int vqb200_proj_fused_backward(int is_lfq, const float* g_out, const float* z, const float* z_e,
+                               int64_t B, int64_t D, int64_t T, const float* W_in, const float* W_out, int64_t d,
+                               const float* g_loss, float entropy_loss_weight, float* g_z, float* grads,
+                               vqb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

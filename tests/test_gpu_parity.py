@@ -241,7 +241,7 @@ def test_hybrid_golden(name):
             z = T(z_np).requires_grad_(True)
         loss, q, met = mod(z)
         idx = N_(mod.vq.last_indices).astype(np.int64)
-        z_e = N_(mod.fsq.project_in(z))
+        z_e = N_(mod.fsq.last_z_e)      # the engine's own post-project_in tensor (fused kernel)
         np.testing.assert_array_equal(N_(mod.fsq.last_indices), fsq_quantize(z_e, levels)["indices"])
         ref = hybrid_forward(z_np, levels, g["init.fsq.project_in.weight"], g["init.fsq.project_in.bias"],
                              g["init.fsq.project_out.weight"], g["init.fsq.project_out.bias"], stages, True,
@@ -335,7 +335,7 @@ def test_cfg2_hybrid_three_steps():
         z = T(np.ascontiguousarray(z_np.transpose(0, 2, 1))).permute(0, 2, 1).requires_grad_(True)
         loss, q, met = mod(z)
         idx = N_(mod.vq.last_indices).astype(np.int64)
-        z_e = N_(mod.fsq.project_in(z))
+        z_e = N_(mod.fsq.last_z_e)      # the engine's own post-project_in tensor (fused kernel)
         np.testing.assert_array_equal(N_(mod.fsq.last_indices), fsq_quantize(z_e, [8, 5, 5, 5])["indices"])
         ref = hybrid_forward(z_np, [8, 5, 5, 5], sd["fsq.project_in.weight"], sd["fsq.project_in.bias"],
                              sd["fsq.project_out.weight"], sd["fsq.project_out.bias"], stages, True,
@@ -365,6 +365,86 @@ def test_cfg3_rvq_chunk():
         g = rng.standard_normal((B, D, Tt)).astype(np.float32)
         flips, _ = _rvq_step(mod, stages, z, g, 1.0)
         print("cfg3 chunk step", step, "benign flips", flips)
+
+
+def _proj_oracle_grads(z, z_q, g, g_ze, w_in, w_out):
+    """Autograd of out = W_out z_q + b_out, z_e = W_in z + b_in with straight-through z_q (float64)."""
+    z, z_q, g, g_ze = (np.asarray(a, np.float64) for a in (z, z_q, g, g_ze))
+    return {"g_z": np.einsum("jc,bjt->bct", np.asarray(w_in, np.float64)[:, :, 0], g_ze),
+            "w_in": np.einsum("bjt,bct->jc", g_ze, z)[:, :, None], "b_in": g_ze.sum((0, 2)),
+            "w_out": np.einsum("bct,bjt->cj", g, z_q)[:, :, None], "b_out": g.sum((0, 2))}
+
+
+@pytest.mark.parametrize("levels,B,Tt", [([8, 5, 5, 5], 4099, 10), ([8, 5, 5, 5], 512, 1), ([7, 5, 5, 5, 5, 3], 333, 7),
+                                         ([3] * 10, 1000, 10), ([2] * 16, 257, 3)])
+def test_fsq_fused_projections(levels, B, Tt):
+    """FSQ module with both 1x1 projections inside the kernel vs the oracle: indices bit-exact
+    from the engine's own z_e, z_e / output / gradients within tolerance, and the unfused path agrees."""
+    from oracle import fsq_forward, conv1x1
+    vq = _mods()
+    D, d = 64, len(levels)
+    torch.manual_seed(5 + d)
+    mod = vq.FSQ(levels, D, D).to(DEV)
+    rng = np.random.default_rng(B + d)
+    z_np = (2.0 * rng.standard_normal((B, D, Tt))).astype(np.float32)
+    g_np = rng.standard_normal((B, D, Tt)).astype(np.float32)
+    sd = {k: N_(v) for k, v in mod.state_dict().items()}
+    z = T(z_np).requires_grad_(True)
+    loss, out, met = mod(z)
+    assert mod.last_z_e is not None and mod.last_z_e.shape == (B, d, Tt)
+    (out * T(g_np)).sum().backward()
+    z_e = N_(mod.last_z_e)
+    assert_close(z_e, conv1x1(z_np, sd["project_in.weight"], sd["project_in.bias"]), TOL, "z_e")
+    ref = fsq_forward(z_np, levels, sd["project_in.weight"], sd["project_in.bias"], sd["project_out.weight"],
+                      sd["project_out.bias"], z_e=z_e)
+    np.testing.assert_array_equal(N_(mod.last_indices), ref["indices"])
+    assert_close(N_(out), ref["quantized"], TOL, "out")
+    assert float(loss) == 0.0
+    assert float(met["perplexity"]) == float(len(np.unique(ref["indices"])))
+    g_ze = np.einsum("cj,bct->bjt", sd["project_out.weight"][:, :, 0].astype(np.float64), g_np.astype(np.float64))
+    og = _proj_oracle_grads(z_np, ref["z_hard"], g_np, g_ze, sd["project_in.weight"], sd["project_out.weight"])
+    assert_close(N_(z.grad), og["g_z"], 1e-4, "g_z")
+    assert_close(N_(mod.project_in.weight.grad), og["w_in"], 1e-4, "g project_in.weight")
+    assert_close(N_(mod.project_in.bias.grad), og["b_in"], 1e-4, "g project_in.bias")
+    assert_close(N_(mod.project_out.weight.grad), og["w_out"], 1e-4, "g project_out.weight")
+    assert_close(N_(mod.project_out.bias.grad), og["b_out"], 1e-4, "g project_out.bias")
+    # stock conv1d + elementwise kernel path: same numbers up to conv rounding
+    mod.fuse_projections = False
+    _, out_u, _ = mod(T(z_np))
+    same = N_(mod.last_indices) == ref["indices"]
+    assert same.mean() > 0.999
+    assert_close(N_(out_u)[same.nonzero()[0]], N_(out)[same.nonzero()[0]], 1e-4, "fused vs unfused")
+
+
+@pytest.mark.parametrize("cd,B,Tt", [(10, 4099, 10), (10, 512, 1), (4, 300, 7), (16, 1000, 3)])
+def test_lfq_fused_projections(cd, B, Tt):
+    from oracle import lfq_quantize, lfq_backward_ze, conv1x1
+    vq = _mods()
+    D = 64
+    torch.manual_seed(11 + cd)
+    mod = vq.LFQ(D, codebook_dim=cd).to(DEV)
+    rng = np.random.default_rng(B + cd)
+    z_np = (2.0 * rng.standard_normal((B, D, Tt))).astype(np.float32)
+    g_np = rng.standard_normal((B, D, Tt)).astype(np.float32)
+    sd = {k: N_(v) for k, v in mod.state_dict().items()}
+    z = T(z_np).requires_grad_(True)
+    loss, out, met = mod(z)
+    ((out * T(g_np)).sum() + 3.0 * loss).backward()
+    z_e = N_(mod.last_z_e)
+    assert_close(z_e, conv1x1(z_np, sd["project_in.weight"], sd["project_in.bias"]), TOL, "z_e")
+    ref = lfq_quantize(z_e, 0.1)
+    np.testing.assert_array_equal(N_(mod.last_indices), ref["indices"])
+    assert_close(N_(out), conv1x1(ref["z_q"], sd["project_out.weight"], sd["project_out.bias"]), TOL, "out")
+    assert abs(float(loss) - float(ref["loss"])) <= 1e-5 * max(1.0, abs(float(ref["loss"])))
+    assert float(met["perplexity"]) == float(len(np.unique(ref["indices"])))
+    g_zq = np.einsum("cj,bct->bjt", sd["project_out.weight"][:, :, 0].astype(np.float64), g_np.astype(np.float64))
+    g_ze = lfq_backward_ze(z_e, g_zq, 3.0, 0.1)
+    og = _proj_oracle_grads(z_np, ref["z_q"], g_np, g_ze, sd["project_in.weight"], sd["project_out.weight"])
+    assert_close(N_(z.grad), og["g_z"], 1e-4, "g_z")
+    assert_close(N_(mod.project_in.weight.grad), og["w_in"], 1e-4, "g project_in.weight")
+    assert_close(N_(mod.project_in.bias.grad), og["b_in"], 1e-4, "g project_in.bias")
+    assert_close(N_(mod.project_out.weight.grad), og["w_out"], 1e-4, "g project_out.weight")
+    assert_close(N_(mod.project_out.bias.grad), og["b_out"], 1e-4, "g project_out.bias")
 
 
 @pytest.mark.parametrize("B,Tt,K,contig", [(4000, 10, 1024, True), (2311, 7, 300, True), (5003, 1, 512, True),
