@@ -6,12 +6,11 @@
 // path moves z_e / z_q through HBM twice more and runs three launches per direction; here the algorithmic bytes are
 // 8D + 4d + 8 per vector forward (read z, write out, write z_e and the int64 index) and 12D + 4d backward.
 //
-// Layout: contiguous [B, 64, T]; a tile is a run of whole samples = one contiguous byte range streamed by bulk-TMA
-// (cp.async.bulk + mbarrier in, cp.async.bulk shared->global out), two stages per CTA.  A row (b,t) is handled by
-// LPR = 64/CPT lanes of one warp (lane kq owns channels kq, kq+LPR, ...: a stride-T walk over shared memory that is
-// bank-conflict free for odd T and T = 2*odd): the D -> d projection is a CPT-term partial dot product
-// per lane plus an xor-butterfly over the lanes of the row (every lane ends with bit-identical sums), the d -> D
-// projection is thread-local.  Projection weights live in registers.
+// Layout: contiguous [B, 64, T]; a tile is a run of whole samples (<= 128 rows) = one contiguous byte range streamed
+// by bulk-TMA (cp.async.bulk + mbarrier in, cp.async.bulk shared->global out).  ONE THREAD PER ROW (b,t): both
+// projections are thread-local dot products (no shuffles), the projection weights are broadcast from shared memory
+// 16 bytes at a time ([channel][DQ] layout).  The backward kernel adds a second phase with one thread per channel
+// that forms the parameter-gradient outer products over the rows of the tile.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "uniq.cuh"
@@ -19,10 +18,10 @@
 namespace vqb200 {
 
 constexpr int F_D = 64;                   // channel count the fused kernels are built for
-constexpr int F_TILE_FWD = 8192;          // forward: 32 KiB tiles (128 rows), 2 stages
-constexpr int F_TILE_BWD = 4096;          // backward: two operands per stage -> 16 KiB tiles
-constexpr int F_NT = 256;
-constexpr int F_STAGES = 2;
+constexpr int F_ROWS = 128;               // rows per tile == threads per CTA
+constexpr int F_TILE = F_ROWS * F_D;      // 8192 floats = 32 KiB
+constexpr int F_NT = F_ROWS;
+constexpr int F_STAGES_FWD = 2;           // forward: two tiles in flight per CTA; backward: one (two operands per tile)
 constexpr int F_MAX_DQ = 16;
 
 struct FusedParams {
@@ -46,50 +45,47 @@ struct FusedParams {
 __device__ __forceinline__ float fsq_round_st(float z) { return __fadd_rn(z, __fsub_rn(rintf(z), z)); }   // :130-131
 __device__ __forceinline__ float lfq_sign_st(float z) { return __fadd_rn(z, __fsub_rn((z > 0.f) ? 1.f : -1.f, z)); }   // :172-174
 
-template <int LPR>
-__device__ __forceinline__ float row_sum(float v) {
-#pragma unroll
-  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+// shared-memory copies of the projection weights, [channel][DQ] so that one 16-byte broadcast load feeds 4 FMAs
+template <int DQ>
+__device__ __forceinline__ void stage_weights(const FusedParams& p, float* sWin, float* sWout, int tid) {
+  for (int i = tid; i < F_D * DQ; i += F_NT) {
+    const int c = i / DQ, j = i - c * DQ;
+    sWin[i] = (j < p.d) ? __ldg(p.W_in + j * F_D + c) : 0.f;       // W_in[j][c]
+    sWout[i] = (j < p.d) ? __ldg(p.W_out + c * p.d + j) : 0.f;     // W_out[c][j]
+  }
 }
 
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
-template <bool IS_LFQ, int DQ, int CPT>
+template <bool IS_LFQ, int DQ>
 __global__ void __launch_bounds__(F_NT)
 fused_forward_kernel(const FusedParams p) {
   using namespace ptx;
-  constexpr int LPR = F_D / CPT;                 // lanes per row
-  constexpr int RPP = F_NT / LPR;                // rows per pass
-  extern __shared__ __align__(128) float smem[];
-  __shared__ uint64_t full[F_STAGES];
+  extern __shared__ __align__(128) float smem[];      // [F_STAGES_FWD][F_TILE]
+  __shared__ uint64_t full[F_STAGES_FWD];
   __shared__ unsigned lbm[Q_LOCAL_WORDS];
+  __shared__ __align__(16) float sWin[F_D * DQ], sWout[F_D * DQ];
+  __shared__ float sBout[F_D];
   const UniqWs w(p.ws);
   const int tid = threadIdx.x;
   const int d = p.d, T = p.T;
-  const int kq = tid % LPR, rsub = tid / LPR;
   const int slab = F_D * T;
 
-  float win[DQ][CPT], wout[CPT][DQ], bin[DQ], bout[CPT], fb[DQ];
+  stage_weights<DQ>(p, sWin, sWout, tid);
+  if (tid < F_D) sBout[tid] = __ldg(p.b_out + tid);
+  float bin[DQ], fb[DQ];
 #pragma unroll
   for (int j = 0; j < DQ; ++j) {
     bin[j] = (j < d) ? __ldg(p.b_in + j) : 0.f;
     fb[j] = (!IS_LFQ && j < d) ? (float)__ldg(p.basis + j) : 0.f;
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-      win[j][c] = (j < d) ? __ldg(p.W_in + j * F_D + kq + c * LPR) : 0.f;
-      wout[c][j] = (j < d) ? __ldg(p.W_out + (kq + c * LPR) * d + j) : 0.f;
-    }
   }
-#pragma unroll
-  for (int c = 0; c < CPT; ++c) bout[c] = __ldg(p.b_out + kq + c * LPR);
-
   if (tid == 0) {
-    for (int s = 0; s < F_STAGES; ++s) mbar_init(smem_u32(full + s), 1);
+    for (int s = 0; s < F_STAGES_FWD; ++s) mbar_init(smem_u32(full + s), 1);
     fence_barrier_init();
   }
   for (int i = tid; i < Q_LOCAL_WORDS; i += F_NT) lbm[i] = 0u;
+  const int bl = tid / T, t = tid - bl * T;       // this thread's row inside every tile
   __syncthreads();
 
   const long long my_tiles = (p.ntiles > blockIdx.x) ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -98,86 +94,84 @@ fused_forward_kernel(const FusedParams p) {
     return (int)min((long long)p.samples_per_tile, p.B - b0);
   };
   auto issue_load = [&](long long i) {           // thread 0 only
-    const int s = (int)(i % F_STAGES);
+    const int s = (int)(i % F_STAGES_FWD);
     const long long b0 = (blockIdx.x + i * gridDim.x) * p.samples_per_tile;
     const uint32_t bytes = (uint32_t)tile_samples(i) * slab * 4;
     mbar_expect_tx(smem_u32(full + s), bytes);
-    bulk_g2s(smem_u32(smem + (size_t)s * F_TILE_FWD), p.z + b0 * slab, bytes, smem_u32(full + s));
+    bulk_g2s(smem_u32(smem + (size_t)s * F_TILE), p.z + b0 * slab, bytes, smem_u32(full + s));
   };
-  if (tid == 0) for (long long i = 0; i < my_tiles && i < F_STAGES - 1; ++i) issue_load(i);
+  if (tid == 0) for (long long i = 0; i < my_tiles && i < F_STAGES_FWD - 1; ++i) issue_load(i);
 
   float ent = 0.f;
   for (long long i = 0; i < my_tiles; ++i) {
-    const int s = (int)(i % F_STAGES);
+    const int s = (int)(i % F_STAGES_FWD);
     const long long b0 = (blockIdx.x + i * gridDim.x) * p.samples_per_tile;
     const int ns = tile_samples(i);
     const int rows = ns * T;
-    float* X = smem + (size_t)s * F_TILE_FWD;
-    if (tid == 0 && i + F_STAGES - 1 < my_tiles) {
+    float* X = smem + (size_t)s * F_TILE;
+    if (tid == 0 && i + F_STAGES_FWD - 1 < my_tiles) {
       bulk_wait_read<0>();                       // the store that last read the other stage has drained it
-      issue_load(i + F_STAGES - 1);
+      issue_load(i + F_STAGES_FWD - 1);
     }
-    mbar_wait(smem_u32(full + s), (uint32_t)((i / F_STAGES) & 1), nullptr, 0);
-    for (int r0 = 0; r0 < rows; r0 += RPP) {     // warp-uniform trip count: the butterfly needs every lane
-      const int r = r0 + rsub;
-      const bool active = r < rows;
-      const int bl = active ? r / T : 0, t = active ? r - bl * T : 0;
-      float* px = X + bl * slab + t + kq * T;
-      float x[CPT], ze[DQ], zh[DQ];
+    mbar_wait(smem_u32(full + s), (uint32_t)((i / F_STAGES_FWD) & 1), nullptr, 0);
+    if (tid < rows) {
+      float* px = X + bl * slab + t;
+      float ze[DQ], zh[DQ];
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) x[c] = active ? px[c * LPR * T] : 0.f;
+      for (int j = 0; j < DQ; ++j) ze[j] = 0.f;
+#pragma unroll
+      for (int c = 0; c < F_D; ++c) {             // z_e = W_in z (+ b_in below)
+        const float x = px[c * T];
+#pragma unroll
+        for (int j4 = 0; j4 < DQ / 4; ++j4) {
+          const float4 wv = *reinterpret_cast<const float4*>(sWin + c * DQ + j4 * 4);
+          ze[j4 * 4 + 0] = fmaf(wv.x, x, ze[j4 * 4 + 0]); ze[j4 * 4 + 1] = fmaf(wv.y, x, ze[j4 * 4 + 1]);
+          ze[j4 * 4 + 2] = fmaf(wv.z, x, ze[j4 * 4 + 2]); ze[j4 * 4 + 3] = fmaf(wv.w, x, ze[j4 * 4 + 3]);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < DQ; ++j) {
-        float a = 0.f;
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) a = fmaf(win[j][c], x[c], a);
-        ze[j] = row_sum<LPR>(a) + bin[j];
+        ze[j] += bin[j];
         zh[j] = IS_LFQ ? lfq_sign_st(ze[j]) : fsq_round_st(ze[j]);
       }
-      if (IS_LFQ && active && kq < d) {
-        // entropy term of component kq (one lane per component); only its mean enters the loss (1e-5 tolerance)
-        // -> MUFU-based fast intrinsics
-        float zk = ze[0];
 #pragma unroll
-        for (int j = 1; j < DQ; ++j) zk = (kq == j) ? ze[j] : zk;
-        const float pr = __fdividef(1.f, 1.f + __expf(-zk));
-        const float q = 1.f - pr;
-        ent -= fmaf(pr, __logf(pr + 1e-6f), q * __logf(q + 1e-6f));
+      for (int c = 0; c < F_D; ++c) {             // out = W_out z_q + b_out, in place over the input tile
+        float o = sBout[c];
+#pragma unroll
+        for (int j4 = 0; j4 < DQ / 4; ++j4) {
+          const float4 wv = *reinterpret_cast<const float4*>(sWout + c * DQ + j4 * 4);
+          o = fmaf(wv.x, zh[j4 * 4 + 0], o); o = fmaf(wv.y, zh[j4 * 4 + 1], o);
+          o = fmaf(wv.z, zh[j4 * 4 + 2], o); o = fmaf(wv.w, zh[j4 * 4 + 3], o);
+        }
+        px[c * T] = o;
       }
-      if (active) {
+      const long long b = b0 + bl;
+      long long code = 0;
+      float sidx = 0.f;
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-          float o = bout[c];
-#pragma unroll
-          for (int j = 0; j < DQ; ++j) o = fmaf(wout[c][j], zh[j], o);
-          px[c * LPR * T] = o;
-        }
-        if (kq == 0) {
-          const long long b = b0 + bl;
-          long long code = 0;
-          float sidx = 0.f;
-#pragma unroll
-          for (int j = 0; j < DQ; ++j) {
-            if (j < d) {
-              p.z_e[(b * d + j) * T + t] = ze[j];
-              if (IS_LFQ) {
-                if (zh[j] > 0.f) code |= (1LL << j);
-              } else {
-                const float pj = __fmul_rn(zh[j], fb[j]);                 // :135 float multiply-sum, then truncate
-                sidx = (j == 0) ? pj : __fadd_rn(sidx, pj);
-              }
-            }
-          }
-          if (!IS_LFQ) code = trunc_to_i64(sidx);
-          p.idx[b * T + t] = code;
-          if (code >= -Q_LOCAL_HALF && code < Q_LOCAL_HALF) {
-            const unsigned bit = (unsigned)(code + Q_LOCAL_HALF);
-            const unsigned m = 1u << (bit & 31);
-            if (!(lbm[bit >> 5] & m)) atomicOr(&lbm[bit >> 5], m);
+      for (int j = 0; j < DQ; ++j) {
+        if (j < d) {
+          p.z_e[(b * d + j) * T + t] = ze[j];
+          if (IS_LFQ) {
+            if (zh[j] > 0.f) code |= (1LL << j);
+            // entropy term: only its mean enters the loss (1e-5 tolerance) -> MUFU-based fast intrinsics
+            const float pr = __fdividef(1.f, 1.f + __expf(-ze[j]));
+            const float q = 1.f - pr;
+            ent -= fmaf(pr, __logf(pr + 1e-6f), q * __logf(q + 1e-6f));
           } else {
-            unique_insert(w, code);
+            const float pj = __fmul_rn(zh[j], fb[j]);                 // :135 float multiply-sum, then truncate
+            sidx = (j == 0) ? pj : __fadd_rn(sidx, pj);
           }
         }
+      }
+      if (!IS_LFQ) code = trunc_to_i64(sidx);
+      p.idx[b * T + t] = code;
+      if (code >= -Q_LOCAL_HALF && code < Q_LOCAL_HALF) {
+        const unsigned bit = (unsigned)(code + Q_LOCAL_HALF);
+        const unsigned m = 1u << (bit & 31);
+        if (!(lbm[bit >> 5] & m)) atomicOr(&lbm[bit >> 5], m);
+      } else {
+        unique_insert(w, code);
       }
     }
     fence_proxy_async();                         // generic-proxy smem writes -> visible to the bulk store
@@ -242,114 +236,124 @@ fused_forward_kernel(const FusedParams p) {
 // backward: g_z = W_in^T g_ze,  g_ze = W_out^T g_out (+ LFQ entropy term);  dW_out = sum g_out (x) z_q,
 // db_out = sum g_out,  dW_in = sum g_ze (x) z,  db_in = sum g_ze.  (autograd of :126-154 / :170-194; the rounding
 // and the sign are straight-through)
+//   phase A1 (thread = row):      g_ze, z_q of the row -> shared memory
+//   phase B  (thread = channel):  outer products over the tile's rows into register accumulators
+//   phase A2 (thread = row):      g_z = W_in^T g_ze, in place over the g_out tile -> bulk store
 // ------------------------------------------------------------------------------------------
-template <bool IS_LFQ, int DQ, int CPT>
+template <bool IS_LFQ, int DQ>
 __global__ void __launch_bounds__(F_NT)
 fused_backward_kernel(const FusedParams p) {
   using namespace ptx;
-  constexpr int LPR = F_D / CPT;
-  constexpr int RPP = F_NT / LPR;
-  constexpr int STAGE_FLOATS = 2 * F_TILE_BWD;    // [g_out tile | z tile]
-  extern __shared__ __align__(128) float smem[];
-  __shared__ uint64_t full[F_STAGES];
-  __shared__ float sacc[2 * F_D * F_MAX_DQ + F_D + F_MAX_DQ];
+  extern __shared__ __align__(128) float smem[];      // [g_out tile | z tile]
+  __shared__ uint64_t full;
+  __shared__ __align__(16) float sWin[F_D * DQ], sWout[F_D * DQ];
+  __shared__ __align__(16) float sGze[F_ROWS * DQ], sZq[F_ROWS * DQ];
+  __shared__ int sOff[F_ROWS];
+  __shared__ float sBin[F_MAX_DQ];
+  float* G = smem;
+  const float* X = smem + F_TILE;
   const int tid = threadIdx.x;
   const int d = p.d, T = p.T;
-  const int kq = tid % LPR, rsub = tid / LPR;
   const int slab = F_D * T;
-  const int nacc = 2 * F_D * d + F_D + d;
 
-  float win[DQ][CPT], wout[CPT][DQ];
-#pragma unroll
-  for (int j = 0; j < DQ; ++j) {
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-      win[j][c] = (j < d) ? __ldg(p.W_in + j * F_D + kq + c * LPR) : 0.f;
-      wout[c][j] = (j < d) ? __ldg(p.W_out + (kq + c * LPR) * d + j) : 0.f;
-    }
-  }
-  float a_win[DQ][CPT] = {}, a_wout[CPT][DQ] = {}, a_bout[CPT] = {}, a_bin[DQ] = {};
+  stage_weights<DQ>(p, sWin, sWout, tid);
+  const int bl = tid / T, t = tid - bl * T;
+  sOff[tid] = bl * slab + t;
+  if (tid < F_MAX_DQ) sBin[tid] = 0.f;
   const float lscale = IS_LFQ ? (p.g_loss ? __ldg(p.g_loss) : 1.f) * (-p.weight / (float)((double)p.B * T * d)) : 0.f;
-
-  if (tid == 0) {
-    for (int s = 0; s < F_STAGES; ++s) mbar_init(smem_u32(full + s), 1);
-    fence_barrier_init();
-  }
-  for (int i = tid; i < nacc; i += F_NT) sacc[i] = 0.f;
+  if (tid == 0) { mbar_init(smem_u32(&full), 1); fence_barrier_init(); }
   __syncthreads();
 
-  const long long my_tiles = (p.ntiles > blockIdx.x) ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  auto tile_samples = [&](long long i) {
-    const long long b0 = (blockIdx.x + i * gridDim.x) * p.samples_per_tile;
-    return (int)min((long long)p.samples_per_tile, p.B - b0);
-  };
-  auto issue_load = [&](long long i) {           // thread 0 only
-    const int s = (int)(i % F_STAGES);
-    const long long b0 = (blockIdx.x + i * gridDim.x) * p.samples_per_tile;
-    const uint32_t bytes = (uint32_t)tile_samples(i) * slab * 4;
-    float* G = smem + (size_t)s * STAGE_FLOATS;
-    mbar_expect_tx(smem_u32(full + s), 2 * bytes);
-    bulk_g2s(smem_u32(G), p.g_out + b0 * slab, bytes, smem_u32(full + s));
-    bulk_g2s(smem_u32(G + F_TILE_BWD), p.z + b0 * slab, bytes, smem_u32(full + s));
-  };
-  if (tid == 0) for (long long i = 0; i < my_tiles && i < F_STAGES - 1; ++i) issue_load(i);
-
-  for (long long i = 0; i < my_tiles; ++i) {
-    const int s = (int)(i % F_STAGES);
-    const long long b0 = (blockIdx.x + i * gridDim.x) * p.samples_per_tile;
-    const int ns = tile_samples(i);
-    const int rows = ns * T;
-    float* G = smem + (size_t)s * STAGE_FLOATS;
-    const float* X = G + F_TILE_BWD;
-    if (tid == 0 && i + F_STAGES - 1 < my_tiles) {
-      bulk_wait_read<0>();
-      issue_load(i + F_STAGES - 1);
-    }
-    mbar_wait(smem_u32(full + s), (uint32_t)((i / F_STAGES) & 1), nullptr, 0);
-    for (int r0 = 0; r0 < rows; r0 += RPP) {
-      const int r = r0 + rsub;
-      const bool active = r < rows;
-      const int bl = active ? r / T : 0, t = active ? r - bl * T : 0;
-      const int off = bl * slab + t + kq * T;
-      float g[CPT], x[CPT], gze[DQ], zq[DQ];
+  // phase B role: channel cB, rows [hB*64, hB*64+64)
+  const int cB = tid & (F_D - 1), hB = tid >> 6;
+  float a_win[DQ], a_wout[DQ], a_bout = 0.f, a_bin[DQ];
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) { g[c] = active ? G[off + c * LPR * T] : 0.f; x[c] = active ? X[off + c * LPR * T] : 0.f; }
-      const float* pze = p.z_e + ((b0 + bl) * d) * T + t;
-      float eterm = 0.f;                          // LFQ: lane kq computes the entropy-gradient term of component kq
-      if (IS_LFQ && active && kq < d) {           // d(-w * mean H_b(sigmoid(z_e)))/dz_e, SURVEY row a14
-        const float zk = __ldg(pze + kq * T);
-        const float dl = 1e-6f;
-        const float pr = 1.f / (1.f + expf(-zk));
-        const float q = 1.f - pr;
-        const float dH = -(logf(pr + dl) + pr / (pr + dl) - logf(q + dl) - q / (q + dl));
-        eterm = lscale * dH * (pr * q);
+  for (int j = 0; j < DQ; ++j) { a_win[j] = 0.f; a_wout[j] = 0.f; a_bin[j] = 0.f; }
+
+  const long long my_tiles = (p.ntiles > blockIdx.x) ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  for (long long i = 0; i < my_tiles; ++i) {
+    const long long b0 = (blockIdx.x + i * gridDim.x) * p.samples_per_tile;
+    const int ns = (int)min((long long)p.samples_per_tile, p.B - b0);
+    const int rows = ns * T;
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)ns * slab * 4;
+      bulk_wait_read<0>();                       // the previous tile's store has drained the buffer
+      mbar_expect_tx(smem_u32(&full), 2 * bytes);
+      bulk_g2s(smem_u32(G), p.g_out + b0 * slab, bytes, smem_u32(&full));
+      bulk_g2s(smem_u32(G + F_TILE), p.z + b0 * slab, bytes, smem_u32(&full));
+    }
+    mbar_wait(smem_u32(&full), (uint32_t)(i & 1), nullptr, 0);
+    // ---- A1 ----
+    float gze[DQ];
+#pragma unroll
+    for (int j = 0; j < DQ; ++j) gze[j] = 0.f;
+    if (tid < rows) {
+      const float* pg = G + bl * slab + t;
+#pragma unroll
+      for (int c = 0; c < F_D; ++c) {
+        const float g = pg[c * T];
+#pragma unroll
+        for (int j4 = 0; j4 < DQ / 4; ++j4) {
+          const float4 wv = *reinterpret_cast<const float4*>(sWout + c * DQ + j4 * 4);
+          gze[j4 * 4 + 0] = fmaf(wv.x, g, gze[j4 * 4 + 0]); gze[j4 * 4 + 1] = fmaf(wv.y, g, gze[j4 * 4 + 1]);
+          gze[j4 * 4 + 2] = fmaf(wv.z, g, gze[j4 * 4 + 2]); gze[j4 * 4 + 3] = fmaf(wv.w, g, gze[j4 * 4 + 3]);
+        }
       }
+      const float* pze = p.z_e + ((b0 + bl) * d) * T + t;
+      float zq[DQ];
 #pragma unroll
       for (int j = 0; j < DQ; ++j) {
-        const float ze = (active && j < d) ? __ldg(pze + j * T) : 0.f;
+        const float ze = (j < d) ? __ldg(pze + j * T) : 0.f;
         zq[j] = (j < d) ? (IS_LFQ ? lfq_sign_st(ze) : fsq_round_st(ze)) : 0.f;
-        float a = 0.f;
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) a = fmaf(wout[c][j], g[c], a);
-        float gj = row_sum<LPR>(a);
-        if (IS_LFQ) gj += __shfl_sync(0xffffffffu, eterm, j, LPR);
-        gze[j] = (active && j < d) ? gj : 0.f;
+        if (IS_LFQ && j < d) {                    // d(-w * mean H_b(sigmoid(z_e)))/dz_e, SURVEY row a14
+          const float dl = 1e-6f;
+          const float pr = 1.f / (1.f + expf(-ze));
+          const float q = 1.f - pr;
+          const float dH = -(logf(pr + dl) + pr / (pr + dl) - logf(q + dl) - q / (q + dl));
+          gze[j] = fmaf(lscale * dH, pr * q, gze[j]);
+        }
+        if (j >= d) gze[j] = 0.f;
+        a_bin[j] += gze[j];
       }
-      if (active) {
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-          float o = 0.f;
+      for (int j4 = 0; j4 < DQ / 4; ++j4) {
+        *reinterpret_cast<float4*>(sGze + tid * DQ + j4 * 4) = make_float4(gze[j4 * 4], gze[j4 * 4 + 1], gze[j4 * 4 + 2], gze[j4 * 4 + 3]);
+        *reinterpret_cast<float4*>(sZq + tid * DQ + j4 * 4) = make_float4(zq[j4 * 4], zq[j4 * 4 + 1], zq[j4 * 4 + 2], zq[j4 * 4 + 3]);
+      }
+    }
+    __syncthreads();
+    // ---- B ----
+    {
+      const int r_end = min(rows, hB * 64 + 64);
+      for (int r = hB * 64; r < r_end; ++r) {
+        const int off = sOff[r] + cB * T;
+        const float gv = G[off], xv = X[off];
+        a_bout += gv;
 #pragma unroll
-          for (int j = 0; j < DQ; ++j) o = fmaf(win[j][c], gze[j], o);
-          G[off + c * LPR * T] = o;                // gradient wrt z, in place over the g_out tile
-          a_bout[c] += g[c];
-#pragma unroll
-          for (int j = 0; j < DQ; ++j) { a_wout[c][j] = fmaf(g[c], zq[j], a_wout[c][j]); a_win[j][c] = fmaf(gze[j], x[c], a_win[j][c]); }
+        for (int j4 = 0; j4 < DQ / 4; ++j4) {
+          const float4 gz = *reinterpret_cast<const float4*>(sGze + r * DQ + j4 * 4);
+          const float4 zq = *reinterpret_cast<const float4*>(sZq + r * DQ + j4 * 4);
+          a_win[j4 * 4 + 0] = fmaf(gz.x, xv, a_win[j4 * 4 + 0]); a_win[j4 * 4 + 1] = fmaf(gz.y, xv, a_win[j4 * 4 + 1]);
+          a_win[j4 * 4 + 2] = fmaf(gz.z, xv, a_win[j4 * 4 + 2]); a_win[j4 * 4 + 3] = fmaf(gz.w, xv, a_win[j4 * 4 + 3]);
+          a_wout[j4 * 4 + 0] = fmaf(gv, zq.x, a_wout[j4 * 4 + 0]); a_wout[j4 * 4 + 1] = fmaf(gv, zq.y, a_wout[j4 * 4 + 1]);
+          a_wout[j4 * 4 + 2] = fmaf(gv, zq.z, a_wout[j4 * 4 + 2]); a_wout[j4 * 4 + 3] = fmaf(gv, zq.w, a_wout[j4 * 4 + 3]);
         }
-        if (kq == 0) {
+      }
+    }
+    __syncthreads();
+    // ---- A2 ----
+    if (tid < rows) {
+      float* pg = G + bl * slab + t;
 #pragma unroll
-          for (int j = 0; j < DQ; ++j) a_bin[j] += gze[j];
+      for (int c = 0; c < F_D; ++c) {
+        float o = 0.f;
+#pragma unroll
+        for (int j4 = 0; j4 < DQ / 4; ++j4) {
+          const float4 wv = *reinterpret_cast<const float4*>(sWin + c * DQ + j4 * 4);
+          o = fmaf(wv.x, gze[j4 * 4 + 0], o); o = fmaf(wv.y, gze[j4 * 4 + 1], o);
+          o = fmaf(wv.z, gze[j4 * 4 + 2], o); o = fmaf(wv.w, gze[j4 * 4 + 3], o);
         }
+        pg[c * T] = o;
       }
     }
     fence_proxy_async();
@@ -361,35 +365,32 @@ fused_backward_kernel(const FusedParams p) {
   }
   if (tid == 0) bulk_wait_all<0>();
 
-  // ---- parameter gradients: registers -> shared (CTA) -> global (one atomic per element per CTA) ----
-  float* s_win = sacc;                       // [d][64]
-  float* s_bin = s_win + d * F_D;            // [d]
-  float* s_wout = s_bin + d;                 // [64][d]
-  float* s_bout = s_wout + F_D * d;          // [64]
-#pragma unroll
-  for (int c = 0; c < CPT; ++c) {
-    const int ch = kq + c * LPR;
-    atomicAdd(s_bout + ch, a_bout[c]);
+  // ---- parameter gradients: registers -> global (one atomic per element per thread; two threads per channel) ----
+  float* g_win = p.grads;                    // [d][64]
+  float* g_bin = g_win + d * F_D;            // [d]
+  float* g_wout = g_bin + d;                 // [64][d]
+  float* g_bout = g_wout + F_D * d;          // [64]
+  if (my_tiles > 0) {
+    atomicAdd(g_bout + cB, a_bout);
 #pragma unroll
     for (int j = 0; j < DQ; ++j) {
-      if (j < d) { atomicAdd(s_win + j * F_D + ch, a_win[j][c]); atomicAdd(s_wout + ch * d + j, a_wout[c][j]); }
+      if (j < d) {
+        atomicAdd(g_win + j * F_D + cB, a_win[j]);
+        atomicAdd(g_wout + cB * d + j, a_wout[j]);
+        atomicAdd(sBin + j, a_bin[j]);
+      }
     }
   }
-  if (kq == 0) {
-#pragma unroll
-    for (int j = 0; j < DQ; ++j) if (j < d) atomicAdd(s_bin + j, a_bin[j]);
-  }
   __syncthreads();
-  for (int i = tid; i < nacc; i += F_NT) { const float v = sacc[i]; if (v != 0.f) atomicAdd(p.grads + i, v); }
+  if (tid < d && my_tiles > 0) atomicAdd(g_bin + tid, sBin[tid]);
 }
 
-static bool fused_geom(const void* a, const void* b, int64_t B, int64_t D, int64_t d, int64_t T, FusedParams& p,
-                       int tile_elems = F_TILE_BWD) {
+static bool fused_geom(const void* a, const void* b, int64_t B, int64_t D, int64_t d, int64_t T, FusedParams& p) {
   if (D != F_D || d < 1 || d > F_MAX_DQ || T < 1 || B < 1) return false;
   if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) return false;
   const long long slab = D * T;
-  if (slab > F_TILE_BWD) return false;
-  p.samples_per_tile = (int)(tile_elems / slab);
+  if (slab > F_TILE) return false;
+  p.samples_per_tile = (int)(F_TILE / slab);
   p.ntiles = (B + p.samples_per_tile - 1) / p.samples_per_tile;
   p.B = B; p.d = (int)d; p.T = (int)T;
   return true;
@@ -397,20 +398,22 @@ static bool fused_geom(const void* a, const void* b, int64_t B, int64_t D, int64
 
 template <bool IS_LFQ, bool BWD>
 static int launch_fused(const FusedParams& p, cudaStream_t stream) {
-  const int per_sm = BWD ? 3 : 3;
-  const int grid = (int)max(1LL, min(p.ntiles, (long long)sm_count() * per_sm));
-  const size_t smem = (size_t)F_STAGES * (BWD ? 2 * F_TILE_BWD : F_TILE_FWD) * sizeof(float);
-#define VQ_FUSED_CASE(DQ, CPT)                                                                                        \
+  const size_t smem = (size_t)(BWD ? 2 : F_STAGES_FWD) * F_TILE * sizeof(float);
+#define VQ_FUSED_CASE(DQ)                                                                                             \
   do {                                                                                                                \
-    auto kern = BWD ? fused_backward_kernel<IS_LFQ, DQ, CPT> : fused_forward_kernel<IS_LFQ, DQ, CPT>;                 \
+    auto kern = BWD ? fused_backward_kernel<IS_LFQ, DQ> : fused_forward_kernel<IS_LFQ, DQ>;                           \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fsq_lfq_fused)");                                 \
-    kern<<<grid, F_NT, smem, stream>>>(p);                                                                            \
+    int per_sm_now = 0;                                                                                               \
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_now, kern, F_NT, smem);                                 \
+    if (e != cudaSuccess || per_sm_now < 1) return cuda_fail(e, "occupancy(fsq_lfq_fused)");                          \
+    const int grid_now = (int)max(1LL, min(p.ntiles, (long long)sm_count() * per_sm_now));                            \
+    kern<<<grid_now, F_NT, smem, stream>>>(p);                                                                            \
   } while (0)
-  if (p.d <= 4) VQ_FUSED_CASE(4, 4);
-  else if (p.d <= 8) VQ_FUSED_CASE(8, 2);
-  else if (p.d <= 12) VQ_FUSED_CASE(12, 2);
-  else VQ_FUSED_CASE(16, 2);
+  if (p.d <= 4) VQ_FUSED_CASE(4);
+  else if (p.d <= 8) VQ_FUSED_CASE(8);
+  else if (p.d <= 12) VQ_FUSED_CASE(12);
+  else VQ_FUSED_CASE(16);
 #undef VQ_FUSED_CASE
   VQ_LAUNCH_CHECK("fsq_lfq_fused_kernel");
   return VQB200_OK;
@@ -438,8 +441,8 @@ int vqb200_fsq_fused_forward(const float* z, int64_t B, int64_t D, int64_t T, co
                "fsq_fused_forward: null pointer");
   VQ_CHECK_ARG(codebook_size > 0, VQB200_EINVAL, "fsq_fused_forward: codebook_size must be positive");
   FusedParams p = {};
-  VQ_CHECK_ARG(fused_geom(z, out, B, D, d, T, p, F_TILE_FWD), VQB200_EUNSUPPORTED,
-               "fsq_fused_forward: needs contiguous 16-byte aligned [B,64,T] with T <= 64 and d <= 16");
+  VQ_CHECK_ARG(fused_geom(z, out, B, D, d, T, p), VQB200_EUNSUPPORTED,
+               "fsq_fused_forward: needs contiguous 16-byte aligned [B,64,T] with T <= 128 and d <= 16");
   p.z = z; p.out = out; p.z_e = z_e; p.idx = (long long*)idx; p.W_in = W_in; p.b_in = b_in; p.W_out = W_out; p.b_out = b_out;
   p.basis = basis; p.codebook_size = (double)codebook_size; p.ws = workspace; p.outm = out2;
   VQ_CUDA(cudaMemsetAsync(workspace, 0, UNIQ_WS_BYTES, stream));
@@ -454,8 +457,8 @@ int vqb200_lfq_fused_forward(const float* z, int64_t B, int64_t D, int64_t T, co
   VQ_CHECK_ARG(z && W_in && b_in && W_out && b_out && out && z_e && idx && workspace && out3, VQB200_EINVAL,
                "lfq_fused_forward: null pointer");
   FusedParams p = {};
-  VQ_CHECK_ARG(fused_geom(z, out, B, D, d, T, p, F_TILE_FWD), VQB200_EUNSUPPORTED,
-               "lfq_fused_forward: needs contiguous 16-byte aligned [B,64,T] with T <= 64 and d <= 16");
+  VQ_CHECK_ARG(fused_geom(z, out, B, D, d, T, p), VQB200_EUNSUPPORTED,
+               "lfq_fused_forward: needs contiguous 16-byte aligned [B,64,T] with T <= 128 and d <= 16");
   p.z = z; p.out = out; p.z_e = z_e; p.idx = (long long*)idx; p.W_in = W_in; p.b_in = b_in; p.W_out = W_out; p.b_out = b_out;
   p.weight = entropy_loss_weight; p.ws = workspace; p.outm = out3;
   VQ_CUDA(cudaMemsetAsync(workspace, 0, UNIQ_WS_BYTES, stream));
@@ -469,7 +472,7 @@ int vqb200_proj_fused_backward(int is_lfq, const float* g_out, const float* z, c
   VQ_CHECK_ARG(g_out && z && z_e && W_in && W_out && g_z && grads, VQB200_EINVAL, "proj_fused_backward: null pointer");
   FusedParams p = {};
   VQ_CHECK_ARG(fused_geom(z, g_z, B, D, d, T, p) && (reinterpret_cast<uintptr_t>(g_out) & 15) == 0, VQB200_EUNSUPPORTED,
-               "proj_fused_backward: needs contiguous 16-byte aligned [B,64,T] with T <= 64 and d <= 16");
+               "proj_fused_backward: needs contiguous 16-byte aligned [B,64,T] with T <= 128 and d <= 16");
   p.z = z; p.g_out = g_out; p.out = g_z; p.z_e = const_cast<float*>(z_e); p.W_in = W_in; p.W_out = W_out;
   p.g_loss = g_loss; p.weight = entropy_loss_weight; p.grads = grads;
   VQ_CUDA(cudaMemsetAsync(grads, 0, vqb200_proj_fused_grad_floats(D, d) * sizeof(float), stream));

@@ -484,7 +484,7 @@ class _ProjFusedFn(torch.autograd.Function):
 
 
 def proj_fused_eligible(z: torch.Tensor, d: int) -> bool:
-    """True when the one-pass kernels apply: contiguous fp32 [B,64,T] (T <= 64) on CUDA and d <= 16."""
+    """True when the one-pass kernels apply: contiguous fp32 [B,64,T] (T <= 128) on CUDA and d <= 16."""
     if z.dim() != 3 or not z.is_cuda or z.dtype != torch.float32 or not z.is_contiguous() or z.shape[0] == 0:
         return False
     B, D, T = z.shape

@@ -194,7 +194,7 @@ int vqb200_lfq_backward(const float* z_e, const float* g_zq, const float* g_loss
                         float entropy_loss_weight, float* g_ze, vqb200_stream_t stream);
 
 /* ---- K5f: FSQ / LFQ with their 1x1 projections fused in ------------ SURVEY.md §8f rank 1 ----
- * One pass over z [B,64,T] (contiguous, 16-byte aligned, T <= 64) for the whole module forward:
+ * One pass over z [B,64,T] (contiguous, 16-byte aligned, T <= 128) for the whole module forward:
  *   FSQ models/vqvae.py:126-154: z_e = W_in z + b_in; z_hard = z_e + (round(z_e) - z_e); idx, metrics as
  *       vqb200_fsq_forward; out = W_out z_hard + b_out.
  *   LFQ models/vqvae.py:170-194: same with the sign instead of the rounding and the entropy loss (out3[0]).
