@@ -446,6 +446,32 @@ def run_extras(torch, vqb200, dev, peaks):
         res["cfg4_lfq_elementwise_n10m"] = {"vectors_per_s": n / (ms * 1e-3), "GBps_algorithmic": n * 88 / (ms * 1e-3) / 1e9,
                                             "frac_of_hbm": n * 88 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
         del ze, zl
+        # cfg4, whole modules with the 1x1 projections fused in: 8D + 4d + 8 bytes / vector forward
+        z4 = 2.0 * torch.randn(B, 64, 10, device=dev)
+        g4 = torch.randn(B, 64, 10, device=dev)
+        for name, m4, dq in (("fsq", vqb200.FSQ([8, 5, 5, 5], 64, 64).to(dev), 4), ("lfq", vqb200.LFQ(64, 10).to(dev), 10)):
+            def f4():
+                with torch.no_grad():
+                    m4(z4)
+            ms = timeit(f4, 10)
+            byts = n * (8 * 64 + 4 * dq + 8)
+            res[f"cfg4_{name}_module_fused_fwd_n10m"] = {"ms": ms, "vectors_per_s": n / (ms * 1e-3), "GBps_algorithmic": byts / (ms * 1e-3) / 1e9,
+                                                         "frac_of_hbm": byts / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+            zz4 = z4.clone().requires_grad_(True)
+
+            def fb4():
+                zz4.grad = None
+                loss, out, _ = m4(zz4)
+                if loss.requires_grad:
+                    torch.autograd.backward([out, loss], [g4, one])
+                else:
+                    out.backward(g4)
+            ms = timeit(fb4, 5)
+            byts = n * (20 * 64 + 8 * dq + 8)
+            res[f"cfg4_{name}_module_fused_fwdbwd_n10m"] = {"ms": ms, "vectors_per_s": n / (ms * 1e-3), "GBps_algorithmic": byts / (ms * 1e-3) / 1e9,
+                                                            "frac_of_hbm": byts / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+            del zz4
+        del z4, g4
         # cfg5 sweep points (assignment kernel K1 alone; N bounded so that the default run stays short).
         # D = 64 / 128 / 256 run the tcgen05 path, D = 512 the exact CUDA-core path.
         for (K5, D5, N5) in ((512, 64, 4_194_304), (4096, 64, 2_097_152), (16384, 64, 1_048_576), (65536, 64, 262_144),

@@ -42,6 +42,10 @@ _SIGNATURES = {
                                          _P, _P, _P, _P, _P, _P]),
     "vqb200_proj_fused_backward": (c_int, [c_int, _P, _P, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P, c_float,
                                            _P, _P, _P]),
+    "vqb200_token_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int64]),
+    "vqb200_tokens_pack": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P]),
+    "vqb200_tokens_unpack": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _P]),
+    "vqb200_tokens_decode": (c_int, [_P, c_int64, _P, _P, _P, c_int64, _P, _P, c_int64, c_int64, c_int64, _P, _P]),
     "vqb200_rvq_output_chain": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                         ctypes.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "vqb200_rvq_small_eligible": (c_int, [c_int64, c_int64, ctypes.c_int32, _P]),

@@ -219,6 +219,26 @@ int vqb200_proj_fused_backward(int is_lfq, const float* g_out, const float* z, c
                                const float* g_loss, float entropy_loss_weight, float* g_z, float* grads,
                                vqb200_stream_t stream);
 
+/* ---- token export / decode-only path -------------------------------- SURVEY.md §8f rank 2 ----
+ * The reference never materialises tokens (scripts/deployment/export_motion.py:25-83 re-runs encoder -> quantizer ->
+ * decoder per window).  A token = S codebook indices of `code_bits` bits (RVQ stages, or the LFQ bit pattern) followed
+ * by d signed FSQ digits of `digit_bits` bits (digit = round(z_e), two's complement, saturated with *overflow = 1;
+ * FSQ rounding is unbounded, models/vqvae.py:127-131, so the mixed-radix index of :135 is not invertible and the
+ * digits are stored instead), little-endian bit stream, rounded up to whole bytes (<= 256 bits).
+ *   codes  int32 [S, B*T];  z_e / digits  fp32 [B, d, T];  tokens  uint8 [B*T, vqb200_token_bytes(...)].
+ * vqb200_tokens_decode rebuilds the quantized latent without the encoder:
+ *   out[b,c,t] = (W_out digits + b_out)[c]  +  ((0 + E_0[i_0][c]) + E_1[i_1][c]) + ...     (:133, :94-98, :229)
+ * E / K are HOST arrays of S device pointers / sizes. */
+int64_t vqb200_token_bytes(int64_t S, int64_t code_bits, int64_t d, int64_t digit_bits);
+int vqb200_tokens_pack(const int32_t* codes, int64_t S, int64_t code_bits, const float* z_e, int64_t d,
+                       int64_t digit_bits, int64_t B, int64_t T, uint8_t* tokens, int32_t* overflow,
+                       vqb200_stream_t stream);
+int vqb200_tokens_unpack(const uint8_t* tokens, int64_t S, int64_t code_bits, int64_t d, int64_t digit_bits,
+                         int64_t B, int64_t T, int32_t* codes, float* digits, vqb200_stream_t stream);
+int vqb200_tokens_decode(const int32_t* codes, int64_t S, const float* const* E, const int64_t* K,
+                         const float* digits, int64_t d, const float* W_out, const float* b_out,
+                         int64_t B, int64_t C, int64_t T, float* out, vqb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -238,6 +238,24 @@ class DualMotionVQVAE(nn.Module):
         y = self.robot_decoder(z_q)
         return {out_key: y.permute(0, 2, 1), "loss_vq": loss_vq, "metrics": metrics, "z_e": z_e}
 
+    # ---- token export / decode-only path (not in the reference) --------------------------
+    def encode_tokens(self, x_human=None, x_robot=None, digit_bits: int = 8):
+        """Motion windows [B, T, dim] -> compact tokens (vqb200.tokens.TokenBatch); eval semantics, no state change."""
+        import vqb200
+        if (x_human is None) == (x_robot is None):
+            raise ValueError("encode_tokens: pass exactly one of x_human / x_robot")
+        enc, x = (self.human_encoder, x_human) if x_human is not None else (self.robot_encoder, x_robot)
+        with torch.no_grad():
+            z_e = enc(x.permute(0, 2, 1))
+        return vqb200.tokens.encode(self.quantizer, z_e.contiguous(), digit_bits=digit_bits)
+
+    def decode_tokens(self, tokens):
+        """Tokens -> robot motion [B, T, robot_dim] through the quantizer's decode-only path and `robot_decoder`."""
+        import vqb200
+        with torch.no_grad():
+            z_q = vqb200.tokens.decode(self.quantizer, tokens)
+            return self.robot_decoder(z_q).permute(0, 2, 1)
+
     def forward(self, x_robot=None, x_human=None):
         outputs = {}
         if x_robot is not None:

@@ -100,3 +100,37 @@ def test_product_path_never_imports_oracle():
                 if f.endswith(".py"):
                     src = open(os.path.join(dirpath, f)).read()
                     assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_token_layout_and_file_format_need_no_gpu(tmp_path):
+    """Token spec per module, the C-ABI size query, the oracle's bit loop and the file round trip (all on CPU)."""
+    import numpy as np
+    import vqb200
+    from vqb200 import tokens
+    from oracle.tokens_oracle import pack, unpack
+    lib = vqb200._lib.load()
+    hy = tokens.spec_for(vqb200.HybridVQ(64, [8, 5, 5, 5], 512), 7, 64, 3)
+    assert (hy.S, hy.code_bits, hy.d, hy.digit_bits, hy.bytes_per_token) == (4, 9, 4, 8, 9)
+    assert tokens.spec_for(vqb200.ResidualVQ(4, 1024, 64), 7, 64, 3).bytes_per_token == 5
+    assert tokens.spec_for(vqb200.VectorQuantizer(1000, 64), 7, 64, 3).code_bits == 10
+    assert tokens.spec_for(vqb200.FSQ([8, 5, 5, 5], 64, 64), 7, 64, 3, digit_bits=6).bytes_per_token == 3
+    assert tokens.spec_for(vqb200.LFQ(64, 10), 7, 64, 3).bytes_per_token == 2
+    with pytest.raises(RuntimeError):
+        tokens.spec_for(vqb200.IdentityVQ(), 1, 64, 1)
+    assert lib.vqb200_token_bytes(4, 9, 4, 8) == 9
+    assert lib.vqb200_token_bytes(0, 0, 0, 0) < 0 and lib.vqb200_token_bytes(8, 32, 16, 32) < 0     # empty / > 256 bits
+    # oracle bit loop is its own inverse, including negative digits
+    rng = np.random.default_rng(3)
+    codes = rng.integers(0, 512, (4, 21))
+    digits = rng.integers(-128, 128, (21, 4))
+    t = pack(codes, digits, 9, 8)
+    c2, d2 = unpack(t, 4, 9, 4, 8)
+    assert np.array_equal(c2, codes) and np.array_equal(d2, digits)
+    # file round trip
+    tb = tokens.TokenBatch(hy, torch.from_numpy(rng.integers(0, 256, (21, 9), dtype=np.uint8)))
+    f = str(tmp_path / "x.vqtok")
+    tokens.save(f, tb)
+    back = tokens.load(f)
+    assert back.spec == hy and torch.equal(back.data, tb.data)
+    with pytest.raises(RuntimeError):
+        tokens.decode(vqb200.HybridVQ(64, [8, 5, 5, 5], 512), back)      # CPU tokens: no CPU path

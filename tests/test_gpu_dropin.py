@@ -142,3 +142,79 @@ def test_graphed_step_matches_eager():
             assert close(a.vq.layers[3].ema_w, b.vq.layers[3].ema_w)
         else:                                   # a benign near-tie flip: realign the eager copy and continue
             b.load_state_dict(a.state_dict())
+
+
+@pytest.mark.parametrize("method", ["vq", "rvq", "fsq", "lfq", "hybrid"])
+def test_token_export_and_decode_only_path(method, tmp_path):
+    """encode -> (file) -> decode reproduces the quantizer's eval output; the packed bytes follow the documented
+    bit layout (numpy bit loop in oracle/tokens_oracle.py)."""
+    import numpy as np
+    import vqb200
+    from vqb200 import tokens
+    from oracle.tokens_oracle import pack
+    torch.manual_seed(3)
+    dev = torch.device("cuda:0")
+    B, D, Tt = 37, 64, 10
+    mod = {"vq": lambda: vqb200.VectorQuantizer(1000, D, use_ema=True),
+           "rvq": lambda: vqb200.ResidualVQ(4, 512, D, use_ema=True),
+           "fsq": lambda: vqb200.FSQ([8, 5, 5, 5], D, D),
+           "lfq": lambda: vqb200.LFQ(D, 10),
+           "hybrid": lambda: vqb200.HybridVQ(D, [8, 5, 5, 5], 512)}[method]().to(dev)
+    with torch.no_grad():
+        for m in mod.modules():
+            if isinstance(m, vqb200.VectorQuantizer):
+                m.embedding.weight.copy_(0.3 * torch.randn_like(m.embedding.weight))
+                m.invalidate_cache()
+    z = 1.5 * torch.randn(B, D, Tt, device=dev)
+    mod.eval()
+    with torch.no_grad():
+        _, q_ref, _ = mod(z)
+    tok = tokens.encode(mod, z)
+    assert int(tok.saturated.item()) == 0
+    sp = tok.spec
+    codes, z_e = tokens._fields(mod, z)
+    digits = None if z_e is None else np.rint(z_e.permute(0, 2, 1).reshape(B * Tt, -1).cpu().numpy()).astype(np.int64)
+    ref_bytes = pack(None if codes is None else codes.cpu().numpy(), digits, sp.code_bits, sp.digit_bits)
+    assert np.array_equal(tok.data.cpu().numpy(), ref_bytes)
+    c2, d2 = tokens.unpack(tok)
+    if codes is not None:
+        assert torch.equal(c2, codes)
+    if z_e is not None:
+        assert torch.equal(d2, torch.round(z_e))
+    f = str(tmp_path / "m.vqtok")
+    tokens.save(f, tok)
+    back = tokens.load(f, device=dev)
+    assert back.spec == sp and torch.equal(back.data, tok.data)
+    q = tokens.decode(mod, back)
+    assert q.shape == q_ref.shape
+    err = float((q - q_ref).abs().max() / q_ref.abs().max())
+    assert err < 1e-5, err
+
+
+def test_token_saturation_is_loud(tmp_path):
+    import vqb200
+    from vqb200 import tokens
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    mod = vqb200.FSQ([8, 5, 5, 5], 64, 64).to(dev)
+    tok = tokens.encode(mod, 4000.0 * torch.randn(5, 64, 3, device=dev), digit_bits=8)
+    assert int(tok.saturated.item()) == 1
+    with pytest.raises(RuntimeError):
+        tokens.save(str(tmp_path / "bad.vqtok"), tok)
+    tok16 = tokens.encode(mod, 4000.0 * torch.randn(5, 64, 3, device=dev), digit_bits=20)
+    assert int(tok16.saturated.item()) == 0
+
+
+def test_model_token_round_trip():
+    """DualMotionVQVAE.encode_tokens / decode_tokens == the eval forward's retargeted output."""
+    from models.vqvae import DualMotionVQVAE
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = DualMotionVQVAE(arch="resnet_no_down", method="hybrid", window_size=10).to(dev).eval()
+    x = torch.randn(6, 10, 263, device=dev)
+    with torch.no_grad():
+        ref = model(x_human=x)["human"]["retargeted"]
+    tok = model.encode_tokens(x_human=x)
+    out = model.decode_tokens(tok)
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max() / ref.abs().max()) < 1e-4
