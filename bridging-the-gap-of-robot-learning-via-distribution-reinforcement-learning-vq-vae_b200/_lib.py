@@ -46,6 +46,8 @@ _SIGNATURES = {
     "vqb200_tokens_pack": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P]),
     "vqb200_tokens_unpack": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, _P, _P]),
     "vqb200_tokens_decode": (c_int, [_P, c_int64, _P, _P, _P, c_int64, _P, _P, c_int64, c_int64, c_int64, _P, _P]),
+    "vqb200_codebook_revive": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, c_float,
+                                       ctypes.c_uint64, _P, _P, _P, c_int64, _P, _P]),
     "vqb200_rvq_output_chain": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                         ctypes.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "vqb200_rvq_small_eligible": (c_int, [c_int64, c_int64, ctypes.c_int32, _P]),

@@ -205,6 +205,42 @@ backward_codebook_kernel(const float* __restrict__ dw1, long long n, const float
 
 __global__ void info_reset_kernel(float* info) { if (threadIdx.x < 4) info[threadIdx.x] = 0.f; }
 
+// ------------------------------------------------------------------------------------------
+// Codebook health (opt-in, NOT in the reference): codes whose usage fell below a threshold are
+// re-seeded from input rows.  The reference suffers 35-90 % dead codes (README.md:353-355) and starts EMA codebooks
+// from ema_w ~ N(0,1) with zero counts (models/vqvae.py:24-26); nothing here runs unless the caller asks for it.
+// Row choice is a pure function of (seed, k): splitmix64(seed + k * golden) mod N.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+codebook_revive_kernel(ZView z, const float* __restrict__ usage, float threshold, unsigned long long seed,
+                       float* __restrict__ E, float* __restrict__ ema_cluster_size, float* __restrict__ ema_w,
+                       int K, int D, int32_t* __restrict__ revived) {
+  // one warp per code
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int k = warp; k < K; k += nwarps) {
+    if (!(usage[k] < threshold)) continue;                  // NaN usage is left alone
+    const long long n = (long long)(splitmix64(seed + (unsigned long long)k * 0x9E3779B97F4A7C15ull) % (unsigned long long)z.N);
+    const float* src = z.p + z.row_base(n);
+    for (int c = lane; c < D; c += 32) {
+      const float v = __ldg(src + (long long)c * z.sC);
+      E[(size_t)k * D + c] = v;
+      if (ema_w) ema_w[(size_t)k * D + c] = v;
+    }
+    if (lane == 0) {
+      if (ema_cluster_size) ema_cluster_size[k] = 1.0f;     // E == ema_w / ema_cluster_size stays consistent
+      atomicAdd(revived, 1);
+    }
+  }
+}
+
 }  // namespace vqb200
 
 using namespace vqb200;
@@ -276,6 +312,23 @@ int vqb200_ema_finalize(const float* stats, float* ema_cluster_size, float* ema_
   ema_finalize_w_kernel<<<grid, 256, 0, stream>>>(dw, ema_w, E, (int)K, (int)D, fd, fo, scratch, ee,
                                                   (unsigned char*)image, info);
   VQ_LAUNCH_CHECK("ema_finalize_w_kernel");
+  return VQB200_OK;
+}
+
+int vqb200_codebook_revive(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,
+                           const float* usage, float threshold, uint64_t seed, float* E, float* ema_cluster_size,
+                           float* ema_w, int64_t K, int32_t* revived, vqb200_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VQ_CHECK_ARG(usage && E && revived, VQB200_EINVAL, "codebook_revive: null pointer");
+  VQ_CHECK_ARG(B >= 0 && C > 0 && T > 0 && K > 0, VQB200_ESHAPE, "codebook_revive: bad shape");
+  VQ_CUDA(cudaMemsetAsync(revived, 0, sizeof(int32_t), stream));
+  if (B * T == 0) return VQB200_OK;
+  VQ_CHECK_ARG(z != nullptr, VQB200_EINVAL, "codebook_revive: null input");
+  const ZView zv = make_zview(z, B, C, T, sB, sC, sT);
+  const int grid = (int)max(1LL, min((long long)(K + 7) / 8, (long long)sm_count() * 4));
+  codebook_revive_kernel<<<grid, 256, 0, stream>>>(zv, usage, threshold, (unsigned long long)seed, E, ema_cluster_size,
+                                                   ema_w, (int)K, (int)C, revived);
+  VQ_LAUNCH_CHECK("codebook_revive_kernel");
   return VQB200_OK;
 }
 

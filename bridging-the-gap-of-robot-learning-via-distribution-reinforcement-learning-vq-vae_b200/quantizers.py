@@ -69,6 +69,34 @@ class VectorQuantizer(nn.Module):
         super()._load_from_state_dict(*args, **kwargs)
         self.invalidate_cache()
 
+    def revive_dead_codes(self, inputs: torch.Tensor, threshold: float = 1e-3, seed: int = 0,
+                          usage: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Opt-in codebook health op (NOT in the reference): every code whose usage
+        (`ema_cluster_size` by default, or the given per-code tensor, e.g. last step's histogram) is below `threshold`
+        is re-seeded from a row of `inputs` [B,C,T] chosen by a hash of (seed, code).  Returns the number of
+        replaced codes as an int32 device tensor (no host sync)."""
+        inputs = _require_cuda(inputs, "VectorQuantizer.revive_dead_codes")
+        if usage is None:
+            if not self.use_ema:
+                raise RuntimeError("revive_dead_codes: pass `usage` for a non-EMA quantizer")
+            usage = self.ema_cluster_size
+        lib = _lib.load()
+        B, C, T = inputs.shape
+        if C != self.embedding_dim:
+            raise RuntimeError(f"revive_dead_codes: channel dim {C} != embedding_dim {self.embedding_dim}")
+        dev = inputs.device
+        revived = torch.zeros(1, dtype=torch.int32, device=dev)
+        sB, sC, sT = inputs.stride()
+        w = self.embedding.weight.detach()
+        with torch.cuda.device(dev):
+            _lib.check(lib.vqb200_codebook_revive(
+                _lib.ptr(inputs.detach()), B, C, T, sB, sC, sT, _lib.ptr(usage.detach().to(torch.float32).contiguous()),
+                _lib.c_float(threshold), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(w),
+                _lib.ptr(self.ema_cluster_size) if self.use_ema else None, _lib.ptr(self.ema_w) if self.use_ema else None,
+                self.num_embeddings, _lib.ptr(revived), _lib.stream_ptr(dev)), "codebook_revive")
+        self.invalidate_cache()
+        return revived
+
     def _config(self, device, plain: bool) -> RVQConfig:
         return RVQConfig([self._state(device)],
                          [self.ema_cluster_size if self.use_ema else None],

@@ -108,6 +108,16 @@ int vqb200_vq_gather_st(const float* z, int64_t B, int64_t C, int64_t T,
                         float* out, float* residual, float* accum, int accum_init,
                         double* sse, vqb200_stream_t stream);
 
+/* ---- codebook health (opt-in, not in the reference) ---------------------- SURVEY.md §8f rank 4 ----
+ * Every code k with usage[k] < threshold (usage = ema_cluster_size, or the histogram of the last step) is re-seeded
+ * from input row n_k = splitmix64(seed + k * 0x9E3779B97F4A7C15) mod N:  E[k] = z[n_k]; if given, ema_w[k] = z[n_k] and
+ * ema_cluster_size[k] = 1.  *revived = number of codes replaced.  The caller must refresh |E|^2 / the tile image
+ * (vqb200_codebook_prepare) afterwards.  Never called by the drop-in modules unless the user asks. */
+int vqb200_codebook_revive(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,
+                           const float* usage, float threshold, uint64_t seed,
+                           float* E, float* ema_cluster_size, float* ema_w, int64_t K,
+                           int32_t* revived, vqb200_stream_t stream);
+
 /* ---- K1 + residual update ------------------- models/vqvae.py:94-98 (r = r - q) then :30-38 --
  * One call per RVQ stage s >= 1:  r_out = r_in - st  with  st = r_in + (E_prev[idx_prev] - r_in)  (bit-identical
  * to the `residual` output of vqb200_vq_gather_st), then idx = argmin_k d(r_out, E_k) as vqb200_vq_assign.

@@ -41,3 +41,34 @@ def unpack(tokens, S: int, code_bits: int, d: int, digit_bits: int):
             digits[n, j] = v - (1 << digit_bits) if v >> (digit_bits - 1) else v
             pos += digit_bits
     return codes, digits
+
+
+# ---- opt-in codebook revive (include/vqb200.h "codebook health"): same hash, numpy --------------------------------
+_M64 = (1 << 64) - 1
+
+
+def splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+def revive(z, E, usage, threshold: float, seed: int, ema_cluster_size=None, ema_w=None):
+    """z [B,C,T]; every code with usage < threshold takes row splitmix64(seed + k*golden) mod N of z."""
+    B, C, T = z.shape
+    rows = np.ascontiguousarray(z.transpose(0, 2, 1)).reshape(B * T, C)
+    E = E.copy()
+    cs = None if ema_cluster_size is None else ema_cluster_size.copy()
+    w = None if ema_w is None else ema_w.copy()
+    n_rev = 0
+    for k in range(E.shape[0]):
+        if usage[k] < threshold:
+            n = splitmix64((seed + k * 0x9E3779B97F4A7C15) & _M64) % (B * T)
+            E[k] = rows[n]
+            if w is not None:
+                w[k] = rows[n]
+            if cs is not None:
+                cs[k] = 1.0
+            n_rev += 1
+    return E, cs, w, n_rev

@@ -210,6 +210,9 @@ def test_model_token_round_trip():
     from models.vqvae import DualMotionVQVAE
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
+    # the stock decoder convolutions must run in true fp32: under TF32 a 1e-7 difference in z_q flips roundings
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     model = DualMotionVQVAE(arch="resnet_no_down", method="hybrid", window_size=10).to(dev).eval()
     x = torch.randn(6, 10, 263, device=dev)
     with torch.no_grad():
@@ -218,3 +221,42 @@ def test_model_token_round_trip():
     out = model.decode_tokens(tok)
     assert out.shape == ref.shape
     assert float((out - ref).abs().max() / ref.abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("use_ema,contig", [(True, True), (True, False), (False, True)])
+def test_revive_dead_codes_is_opt_in_and_deterministic(use_ema, contig):
+    """Codebook health op: bit-identical to the numpy restatement, never runs by itself."""
+    import numpy as np
+    import vqb200
+    from oracle.tokens_oracle import revive
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2)
+    K, D, B, Tt = 256, 64, 33, 7
+    mod = vqb200.VectorQuantizer(K, D, use_ema=use_ema).to(dev)
+    z = torch.randn(B, D, Tt, device=dev) if contig else torch.randn(B, Tt, D, device=dev).permute(0, 2, 1)
+    usage = torch.rand(K, device=dev)
+    if use_ema:
+        mod.ema_cluster_size.copy_(usage)
+    E0 = mod.embedding.weight.detach().cpu().numpy().copy()
+    # a plain forward never revives anything
+    mod.eval()
+    with torch.no_grad():
+        mod(z)
+    assert np.array_equal(mod.embedding.weight.detach().cpu().numpy(), E0)
+    n = mod.revive_dead_codes(z, threshold=0.25, seed=77, usage=None if use_ema else usage)
+    E_ref, cs_ref, w_ref, n_ref = revive(z.cpu().numpy(), E0, usage.cpu().numpy(), 0.25, 77,
+                                          mod.ema_cluster_size.cpu().numpy() * 0 + usage.cpu().numpy() if use_ema else None,
+                                          None)
+    assert int(n.item()) == n_ref and 0 < n_ref < K
+    assert np.array_equal(mod.embedding.weight.detach().cpu().numpy(), E_ref)
+    if use_ema:
+        assert np.array_equal(mod.ema_cluster_size.cpu().numpy(), cs_ref)
+        dead = usage.cpu().numpy() < 0.25
+        assert np.array_equal(mod.ema_w.cpu().numpy()[dead], E_ref[dead])
+    # the derived state (|E|^2, tile image) was invalidated: the next assignment sees the new codes
+    with torch.no_grad():
+        mod(z)
+    d = ((z.permute(0, 2, 1).reshape(-1, 1, D) - mod.embedding.weight.detach()[None]) ** 2).sum(-1)
+    # (two dead codes may hash to the same row -> duplicate codes -> exact ties: compare distances, not indices)
+    got = d.gather(1, mod.last_indices.reshape(-1, 1).long()).squeeze(1)
+    assert float((got - d.min(1).values).abs().max()) < 1e-4
