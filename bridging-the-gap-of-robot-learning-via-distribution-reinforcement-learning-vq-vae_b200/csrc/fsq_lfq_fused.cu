@@ -7,10 +7,15 @@
 // 8D + 4d + 8 per vector forward (read z, write out, write z_e and the int64 index) and 12D + 4d backward.
 //
 // Layout: contiguous [B, 64, T]; a tile is a run of whole samples (<= 128 rows) = one contiguous byte range streamed
-// by bulk-TMA (cp.async.bulk + mbarrier in, cp.async.bulk shared->global out).  ONE THREAD PER ROW (b,t): both
-// projections are thread-local dot products (no shuffles), the projection weights are broadcast from shared memory
-// 16 bytes at a time ([channel][DQ] layout).  The backward kernel adds a second phase with one thread per channel
-// that forms the parameter-gradient outer products over the rows of the tile.
+// by bulk-TMA (cp.async.bulk + mbarrier in, cp.async.bulk shared->global out).  TWO THREADS PER ROW (b,t), adjacent
+// lanes, 32 channels each: the D -> d projection is a thread-local dot product plus ONE shuffle, the d -> D projection
+// is thread-local; the projection weights are broadcast from shared memory
+// 16 bytes at a time ([channel][DQ] layout).  A thread walks its row's channels ROTATED by its sample index inside the
+// tile (channel (c + bl) mod 64 at step c): element (row r, channel c) of the [B,C,T] tile sits at word
+// bl*64*T + t + c*T, so the 32 rows of a warp then touch banks r + c*T -- conflict-free for every T, where the
+// straight walk is 4-way conflicted at T = 10 and 32-way at T = 1.  (The summation order of a projection therefore
+// depends on the row's position in the tile; the results differ in the last bit only.)  The backward kernel adds a
+// second phase with one thread per channel that forms the parameter-gradient outer products over the tile's rows.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "uniq.cuh"
@@ -18,9 +23,9 @@
 namespace vqb200 {
 
 constexpr int F_D = 64;                   // channel count the fused kernels are built for
-constexpr int F_ROWS = 128;               // rows per tile == threads per CTA
+constexpr int F_ROWS = 128;               // rows per tile; two threads per row (even / odd steps of the channel walk)
 constexpr int F_TILE = F_ROWS * F_D;      // 8192 floats = 32 KiB
-constexpr int F_NT = F_ROWS;
+constexpr int F_NT = 2 * F_ROWS;
 constexpr int F_STAGES_FWD = 2;           // forward: two tiles in flight per CTA; backward: one (two operands per tile)
 constexpr int F_MAX_DQ = 16;
 
@@ -59,7 +64,7 @@ __device__ __forceinline__ void stage_weights(const FusedParams& p, float* sWin,
 // forward
 // ------------------------------------------------------------------------------------------
 template <bool IS_LFQ, int DQ>
-__global__ void __launch_bounds__(F_NT)
+__global__ void __launch_bounds__(F_NT, 2)
 fused_forward_kernel(const FusedParams p) {
   using namespace ptx;
   extern __shared__ __align__(128) float smem[];      // [F_STAGES_FWD][F_TILE]
@@ -85,7 +90,8 @@ fused_forward_kernel(const FusedParams p) {
     fence_barrier_init();
   }
   for (int i = tid; i < Q_LOCAL_WORDS; i += F_NT) lbm[i] = 0u;
-  const int bl = tid / T, t = tid - bl * T;       // this thread's row inside every tile
+  const int row = tid >> 1, h = tid & 1;          // this thread's row inside every tile, and its half of the walk
+  const int bl = row / T, t = row - bl * T;
   __syncthreads();
 
   const long long my_tiles = (p.ntiles > blockIdx.x) ? (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -114,36 +120,41 @@ fused_forward_kernel(const FusedParams p) {
       issue_load(i + F_STAGES_FWD - 1);
     }
     mbar_wait(smem_u32(full + s), (uint32_t)((i / F_STAGES_FWD) & 1), nullptr, 0);
-    if (tid < rows) {
-      float* px = X + bl * slab + t;
+    {
+      const bool active = row < rows;             // warp-uniform up to the last partial pair: the shuffle needs every lane
+      float* px = X + (active ? bl * slab + t : 0);
       float ze[DQ], zh[DQ];
 #pragma unroll
       for (int j = 0; j < DQ; ++j) ze[j] = 0.f;
 #pragma unroll
-      for (int c = 0; c < F_D; ++c) {             // z_e = W_in z (+ b_in below)
-        const float x = px[c * T];
+      for (int i = 0; i < F_D / 2; ++i) {         // z_e = W_in z (+ b_in below): this thread's 32 channels
+        const int cr = (2 * i + h + bl) & (F_D - 1);
+        const float x = active ? px[cr * T] : 0.f;
 #pragma unroll
         for (int j4 = 0; j4 < DQ / 4; ++j4) {
-          const float4 wv = *reinterpret_cast<const float4*>(sWin + c * DQ + j4 * 4);
+          const float4 wv = *reinterpret_cast<const float4*>(sWin + cr * DQ + j4 * 4);
           ze[j4 * 4 + 0] = fmaf(wv.x, x, ze[j4 * 4 + 0]); ze[j4 * 4 + 1] = fmaf(wv.y, x, ze[j4 * 4 + 1]);
           ze[j4 * 4 + 2] = fmaf(wv.z, x, ze[j4 * 4 + 2]); ze[j4 * 4 + 3] = fmaf(wv.w, x, ze[j4 * 4 + 3]);
         }
       }
 #pragma unroll
       for (int j = 0; j < DQ; ++j) {
+        ze[j] += __shfl_xor_sync(0xffffffffu, ze[j], 1);          // the partner's 32 channels (bit-identical in both)
         ze[j] += bin[j];
         zh[j] = IS_LFQ ? lfq_sign_st(ze[j]) : fsq_round_st(ze[j]);
       }
+      if (active) {
 #pragma unroll
-      for (int c = 0; c < F_D; ++c) {             // out = W_out z_q + b_out, in place over the input tile
-        float o = sBout[c];
+      for (int i = 0; i < F_D / 2; ++i) {         // out = W_out z_q + b_out, in place over the input tile
+        const int cr = (2 * i + h + bl) & (F_D - 1);
+        float o = sBout[cr];
 #pragma unroll
         for (int j4 = 0; j4 < DQ / 4; ++j4) {
-          const float4 wv = *reinterpret_cast<const float4*>(sWout + c * DQ + j4 * 4);
+          const float4 wv = *reinterpret_cast<const float4*>(sWout + cr * DQ + j4 * 4);
           o = fmaf(wv.x, zh[j4 * 4 + 0], o); o = fmaf(wv.y, zh[j4 * 4 + 1], o);
           o = fmaf(wv.z, zh[j4 * 4 + 2], o); o = fmaf(wv.w, zh[j4 * 4 + 3], o);
         }
-        px[c * T] = o;
+        px[cr * T] = o;
       }
       const long long b = b0 + bl;
       long long code = 0;
@@ -151,13 +162,17 @@ fused_forward_kernel(const FusedParams p) {
 #pragma unroll
       for (int j = 0; j < DQ; ++j) {
         if (j < d) {
-          p.z_e[(b * d + j) * T + t] = ze[j];
+          if ((j & 1) == h) {                     // the pair splits the per-component work
+            p.z_e[(b * d + j) * T + t] = ze[j];
+            if (IS_LFQ) {
+              // entropy term: only its mean enters the loss (1e-5 tolerance) -> MUFU-based fast intrinsics
+              const float pr = __fdividef(1.f, 1.f + __expf(-ze[j]));
+              const float q = 1.f - pr;
+              ent -= fmaf(pr, __logf(pr + 1e-6f), q * __logf(q + 1e-6f));
+            }
+          }
           if (IS_LFQ) {
             if (zh[j] > 0.f) code |= (1LL << j);
-            // entropy term: only its mean enters the loss (1e-5 tolerance) -> MUFU-based fast intrinsics
-            const float pr = __fdividef(1.f, 1.f + __expf(-ze[j]));
-            const float q = 1.f - pr;
-            ent -= fmaf(pr, __logf(pr + 1e-6f), q * __logf(q + 1e-6f));
           } else {
             const float pj = __fmul_rn(zh[j], fb[j]);                 // :135 float multiply-sum, then truncate
             sidx = (j == 0) ? pj : __fadd_rn(sidx, pj);
@@ -165,13 +180,16 @@ fused_forward_kernel(const FusedParams p) {
         }
       }
       if (!IS_LFQ) code = trunc_to_i64(sidx);
-      p.idx[b * T + t] = code;
-      if (code >= -Q_LOCAL_HALF && code < Q_LOCAL_HALF) {
-        const unsigned bit = (unsigned)(code + Q_LOCAL_HALF);
-        const unsigned m = 1u << (bit & 31);
-        if (!(lbm[bit >> 5] & m)) atomicOr(&lbm[bit >> 5], m);
-      } else {
-        unique_insert(w, code);
+      if (h == 0) {
+        p.idx[b * T + t] = code;
+        if (code >= -Q_LOCAL_HALF && code < Q_LOCAL_HALF) {
+          const unsigned bit = (unsigned)(code + Q_LOCAL_HALF);
+          const unsigned m = 1u << (bit & 31);
+          if (!(lbm[bit >> 5] & m)) atomicOr(&lbm[bit >> 5], m);
+        } else {
+          unique_insert(w, code);
+        }
+      }
       }
     }
     fence_proxy_async();                         // generic-proxy smem writes -> visible to the bulk store
@@ -241,7 +259,7 @@ fused_forward_kernel(const FusedParams p) {
 //   phase A2 (thread = row):      g_z = W_in^T g_ze, in place over the g_out tile -> bulk store
 // ------------------------------------------------------------------------------------------
 template <bool IS_LFQ, int DQ>
-__global__ void __launch_bounds__(F_NT)
+__global__ void __launch_bounds__(F_NT, 2)
 fused_backward_kernel(const FusedParams p) {
   using namespace ptx;
   extern __shared__ __align__(128) float smem[];      // [g_out tile | z tile]
@@ -249,6 +267,7 @@ fused_backward_kernel(const FusedParams p) {
   __shared__ __align__(16) float sWin[F_D * DQ], sWout[F_D * DQ];
   __shared__ __align__(16) float sGze[F_ROWS * DQ], sZq[F_ROWS * DQ];
   __shared__ int sOff[F_ROWS];
+  __shared__ __align__(16) float sZe[F_ROWS * F_MAX_DQ];   // z_e slab of the tile ([sample][d][T], as in global memory)
   __shared__ float sBin[F_MAX_DQ];
   float* G = smem;
   const float* X = smem + F_TILE;
@@ -257,14 +276,15 @@ fused_backward_kernel(const FusedParams p) {
   const int slab = F_D * T;
 
   stage_weights<DQ>(p, sWin, sWout, tid);
-  const int bl = tid / T, t = tid - bl * T;
-  sOff[tid] = bl * slab + t;
+  const int row = tid >> 1, h = tid & 1;
+  const int bl = row / T, t = row - bl * T;
+  if (h == 0) sOff[row] = bl * slab + t;
   if (tid < F_MAX_DQ) sBin[tid] = 0.f;
   const float lscale = IS_LFQ ? (p.g_loss ? __ldg(p.g_loss) : 1.f) * (-p.weight / (float)((double)p.B * T * d)) : 0.f;
   if (tid == 0) { mbar_init(smem_u32(&full), 1); fence_barrier_init(); }
   __syncthreads();
 
-  // phase B role: channel cB, rows [hB*64, hB*64+64)
+  // phase B role: channel cB, rows [hB*32, hB*32+32)
   const int cB = tid & (F_D - 1), hB = tid >> 6;
   float a_win[DQ], a_wout[DQ], a_bout = 0.f, a_bin[DQ];
 #pragma unroll
@@ -282,30 +302,35 @@ fused_backward_kernel(const FusedParams p) {
       bulk_g2s(smem_u32(G), p.g_out + b0 * slab, bytes, smem_u32(&full));
       bulk_g2s(smem_u32(G + F_TILE), p.z + b0 * slab, bytes, smem_u32(&full));
     }
+    // the tile's z_e slab (any size / alignment): plain loads that overlap the bulk copies above
+    for (int e = tid; e < ns * d * T; e += F_NT) sZe[e] = __ldg(p.z_e + b0 * d * T + e);
     mbar_wait(smem_u32(&full), (uint32_t)(i & 1), nullptr, 0);
+    __syncthreads();
     // ---- A1 ----
     float gze[DQ];
 #pragma unroll
     for (int j = 0; j < DQ; ++j) gze[j] = 0.f;
-    if (tid < rows) {
-      const float* pg = G + bl * slab + t;
+    const bool active = row < rows;
+    {
+      const float* pg = G + (active ? bl * slab + t : 0);
 #pragma unroll
-      for (int c = 0; c < F_D; ++c) {
-        const float g = pg[c * T];
+      for (int i = 0; i < F_D / 2; ++i) {
+        const int cr = (2 * i + h + bl) & (F_D - 1);
+        const float g = active ? pg[cr * T] : 0.f;
 #pragma unroll
         for (int j4 = 0; j4 < DQ / 4; ++j4) {
-          const float4 wv = *reinterpret_cast<const float4*>(sWout + c * DQ + j4 * 4);
+          const float4 wv = *reinterpret_cast<const float4*>(sWout + cr * DQ + j4 * 4);
           gze[j4 * 4 + 0] = fmaf(wv.x, g, gze[j4 * 4 + 0]); gze[j4 * 4 + 1] = fmaf(wv.y, g, gze[j4 * 4 + 1]);
           gze[j4 * 4 + 2] = fmaf(wv.z, g, gze[j4 * 4 + 2]); gze[j4 * 4 + 3] = fmaf(wv.w, g, gze[j4 * 4 + 3]);
         }
       }
-      const float* pze = p.z_e + ((b0 + bl) * d) * T + t;
+      const float* pze = sZe + (active ? bl : 0) * d * T + t;
       float zq[DQ];
 #pragma unroll
       for (int j = 0; j < DQ; ++j) {
-        const float ze = (j < d) ? __ldg(pze + j * T) : 0.f;
+        const float ze = (active && j < d) ? pze[j * T] : 0.f;
         zq[j] = (j < d) ? (IS_LFQ ? lfq_sign_st(ze) : fsq_round_st(ze)) : 0.f;
-        if (IS_LFQ && j < d) {                    // d(-w * mean H_b(sigmoid(z_e)))/dz_e, SURVEY row a14
+        if (IS_LFQ && j < d && (j & 1) == h) {    // d(-w * mean H_b(sigmoid(z_e)))/dz_e, SURVEY row a14 (the pair splits the components)
           // MUFU-based intrinsics: the term is scaled by w/M and added to the straight-through gradient, its ~1e-6
           // relative error is far inside the 1e-5 tolerance
           const float dl = 1e-6f;
@@ -314,20 +339,23 @@ fused_backward_kernel(const FusedParams p) {
           const float dH = -(__logf(pr + dl) + __fdividef(pr, pr + dl) - __logf(q + dl) - __fdividef(q, q + dl));
           gze[j] = fmaf(lscale * dH, pr * q, gze[j]);
         }
-        if (j >= d) gze[j] = 0.f;
-        a_bin[j] += gze[j];
+        gze[j] += __shfl_xor_sync(0xffffffffu, gze[j], 1);        // the partner's 32 channels and its entropy terms
+        if (j >= d || !active) gze[j] = 0.f;
+        if (h == 0) a_bin[j] += gze[j];
       }
+      if (active && h == 0) {
 #pragma unroll
-      for (int j4 = 0; j4 < DQ / 4; ++j4) {
-        *reinterpret_cast<float4*>(sGze + tid * DQ + j4 * 4) = make_float4(gze[j4 * 4], gze[j4 * 4 + 1], gze[j4 * 4 + 2], gze[j4 * 4 + 3]);
-        *reinterpret_cast<float4*>(sZq + tid * DQ + j4 * 4) = make_float4(zq[j4 * 4], zq[j4 * 4 + 1], zq[j4 * 4 + 2], zq[j4 * 4 + 3]);
+        for (int j4 = 0; j4 < DQ / 4; ++j4) {
+          *reinterpret_cast<float4*>(sGze + row * DQ + j4 * 4) = make_float4(gze[j4 * 4], gze[j4 * 4 + 1], gze[j4 * 4 + 2], gze[j4 * 4 + 3]);
+          *reinterpret_cast<float4*>(sZq + row * DQ + j4 * 4) = make_float4(zq[j4 * 4], zq[j4 * 4 + 1], zq[j4 * 4 + 2], zq[j4 * 4 + 3]);
+        }
       }
     }
     __syncthreads();
     // ---- B ----
     {
-      const int r_end = min(rows, hB * 64 + 64);
-      for (int r = hB * 64; r < r_end; ++r) {
+      const int r_end = min(rows, hB * 32 + 32);
+      for (int r = hB * 32; r < r_end; ++r) {
         const int off = sOff[r] + cB * T;
         const float gv = G[off], xv = X[off];
         a_bout += gv;
@@ -344,18 +372,19 @@ fused_backward_kernel(const FusedParams p) {
     }
     __syncthreads();
     // ---- A2 ----
-    if (tid < rows) {
+    if (active) {
       float* pg = G + bl * slab + t;
 #pragma unroll
-      for (int c = 0; c < F_D; ++c) {
+      for (int i = 0; i < F_D / 2; ++i) {
+        const int cr = (2 * i + h + bl) & (F_D - 1);
         float o = 0.f;
 #pragma unroll
         for (int j4 = 0; j4 < DQ / 4; ++j4) {
-          const float4 wv = *reinterpret_cast<const float4*>(sWin + c * DQ + j4 * 4);
+          const float4 wv = *reinterpret_cast<const float4*>(sWin + cr * DQ + j4 * 4);
           o = fmaf(wv.x, gze[j4 * 4 + 0], o); o = fmaf(wv.y, gze[j4 * 4 + 1], o);
           o = fmaf(wv.z, gze[j4 * 4 + 2], o); o = fmaf(wv.w, gze[j4 * 4 + 3], o);
         }
-        pg[c * T] = o;
+        pg[cr * T] = o;
       }
     }
     fence_proxy_async();
@@ -367,7 +396,7 @@ fused_backward_kernel(const FusedParams p) {
   }
   if (tid == 0) bulk_wait_all<0>();
 
-  // ---- parameter gradients: registers -> global (one atomic per element per thread; two threads per channel) ----
+  // ---- parameter gradients: registers -> global (one atomic per element per thread; four threads per channel) ----
   float* g_win = p.grads;                    // [d][64]
   float* g_bin = g_win + d * F_D;            // [d]
   float* g_wout = g_bin + d;                 // [64][d]
