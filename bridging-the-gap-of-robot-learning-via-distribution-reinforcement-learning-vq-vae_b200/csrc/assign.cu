@@ -6,7 +6,7 @@
 namespace vqb200 {
 int launch_assign_simt(const ZView& z, const float* E, const float* ee, int K, int D,
                        int32_t* idx, float* best, const int32_t* row_list, const int32_t* row_count,
-                       long long max_rows, cudaStream_t stream);
+                       long long max_rows, cudaStream_t stream, unsigned long long* keys = nullptr);
 bool assign_tc_eligible(const ZView& z, int K, int D);
 int launch_assign_tc(const ZView& z, const float* E, const float* ee, const void* image, const float* info,
                      int K, int D, int32_t* idx, float* best, void* workspace, size_t workspace_bytes,

@@ -10,6 +10,9 @@
 //
 // Tiling: CTA = 64 rows x 128 codes, 256 threads, 4x8 register tile per thread, z tile resident in
 // shared memory for the whole codebook sweep, codebook streamed in 128x16 chunks (register prefetch).
+// Short work lists (the latency configs: a few hundred unproven rows) would occupy a handful of SMs for a whole
+// codebook sweep each; there the sweep is split over `splits` CTAs per row tile, which merge through one 64-bit
+// atomicMin per row on a key (ordered distance bits << 32 | index) that encodes exactly the cand_better order.
 #include "common.cuh"
 #include <limits.h>
 
@@ -22,10 +25,33 @@ constexpr int LDZ = BM + 4;
 constexpr int LDE = BN + 4;
 }  // namespace simt
 
+// (distance, index) -> 64-bit key whose unsigned order is the cand_better order: NaN first, then ascending
+// distance (-0 == +0), ties by ascending index.
+__device__ __forceinline__ unsigned long long cand_key(float d, int i) {
+  unsigned u;
+  if (d != d) u = 0u;
+  else {
+    if (d == 0.f) d = 0.f;
+    u = __float_as_uint(d);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    if (u == 0u) u = 1u;                           // keep 0 for NaN only (-NaN bit patterns never reach here)
+  }
+  return ((unsigned long long)u << 32) | (unsigned)i;
+}
+
+__global__ void __launch_bounds__(256)
+assign_keys_finalize_kernel(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ row_list,
+                            const int32_t* __restrict__ row_count, int32_t* __restrict__ idx_out) {
+  const int total = *row_count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    idx_out[row_list[i]] = (int32_t)(keys[i] & 0xFFFFFFFFull);
+}
+
 __global__ void __launch_bounds__(simt::NT, 2)
 vq_assign_simt_kernel(ZView z, const float* __restrict__ E, const float* __restrict__ ee,
                       int K, int D, int Dp, int32_t* __restrict__ idx_out, float* __restrict__ best_out,
-                      const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count) {
+                      const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count,
+                      int splits, unsigned long long* __restrict__ keys) {
   using namespace simt;
   extern __shared__ __align__(16) float smem[];
   float* zs = smem;                    // [Dp][LDZ]   k-major z tile
@@ -39,7 +65,10 @@ vq_assign_simt_kernel(ZView z, const float* __restrict__ E, const float* __restr
   const long long ntiles = (total + BM - 1) / BM;
   const bool vecE = ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(E) & 15) == 0);
 
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const int Kc = (K + splits - 1) / splits;            // codes per split, a multiple of BN when splits > 1
+  for (long long w = blockIdx.x; w < ntiles * splits; w += gridDim.x) {
+    const long long tile = w / splits;
+    const int c_begin = (int)(w - tile * splits) * Kc, c_end = min(K, c_begin + Kc);
     const long long n0 = tile * BM;
     const int rows = (int)min((long long)BM, total - n0);
 
@@ -66,7 +95,7 @@ vq_assign_simt_kernel(ZView z, const float* __restrict__ E, const float* __restr
 #pragma unroll
     for (int i = 0; i < TM; ++i) { best[i] = INFINITY; bidx[i] = INT_MAX; }
 
-    for (int c0 = 0; c0 < K; c0 += BN) {
+    for (int c0 = c_begin; c0 < c_end; c0 += BN) {
       float acc[TM][TN];
 #pragma unroll
       for (int i = 0; i < TM; ++i)
@@ -148,9 +177,13 @@ vq_assign_simt_kernel(ZView z, const float* __restrict__ E, const float* __restr
       }
       const int r = ty * TM + i;
       if (tx == 0 && r < rows) {
-        const long long n = row_list ? (long long)row_list[n0 + r] : n0 + r;
-        idx_out[n] = bidx[i];
-        if (best_out) best_out[n] = best[i];
+        if (keys) {
+          atomicMin(keys + n0 + r, cand_key(best[i], bidx[i]));
+        } else {
+          const long long n = row_list ? (long long)row_list[n0 + r] : n0 + r;
+          idx_out[n] = bidx[i];
+          if (best_out) best_out[n] = best[i];
+        }
       }
     }
   }
@@ -165,7 +198,7 @@ size_t assign_simt_smem_bytes(int D) {
 // row_list == nullptr: all rows of the view.  Otherwise *row_count rows listed in row_list.
 int launch_assign_simt(const ZView& z, const float* E, const float* ee, int K, int D,
                        int32_t* idx, float* best, const int32_t* row_list, const int32_t* row_count,
-                       long long max_rows, cudaStream_t stream) {
+                       long long max_rows, cudaStream_t stream, unsigned long long* keys) {
   using namespace simt;
   const size_t smem = assign_simt_smem_bytes(D);
   VQ_CHECK_ARG(smem <= 227 * 1024, VQB200_ESHAPE, "vq_assign(SIMT): D=%d needs %zu B of shared memory (max 232448)", D, smem);
@@ -176,9 +209,21 @@ int launch_assign_simt(const ZView& z, const float* E, const float* ee, int K, i
   }
   const int Dp = (D + BK - 1) / BK * BK;
   const long long tiles = (max_rows + BM - 1) / BM;
-  const int grid = (int)max(1LL, min(tiles, (long long)sm_count() * 2));
-  vq_assign_simt_kernel<<<grid, NT, smem, stream>>>(z, E, ee, K, D, Dp, idx, best, row_list, row_count);
+  // split the codebook sweep when the caller provides the merge keys (short work lists, see the header comment)
+  int splits = 1;
+  if (keys && row_list && !best) {
+    while (splits < 8 && (K / (splits * 2)) >= BN && (K % (splits * 2 * BN)) == 0) splits *= 2;
+  }
+  if (splits > 1) VQ_CUDA(cudaMemsetAsync(keys, 0xFF, (size_t)max_rows * sizeof(unsigned long long), stream));
+  else keys = nullptr;
+  const int grid = (int)max(1LL, min(tiles * splits, (long long)sm_count() * 2));
+  vq_assign_simt_kernel<<<grid, NT, smem, stream>>>(z, E, ee, K, D, Dp, idx, best, row_list, row_count, splits, keys);
   VQ_LAUNCH_CHECK("vq_assign_simt_kernel");
+  if (splits > 1) {
+    assign_keys_finalize_kernel<<<(int)max(1LL, min((max_rows + 255) / 256, (long long)sm_count())), 256, 0, stream>>>(
+        keys, row_list, row_count, idx);
+    VQ_LAUNCH_CHECK("assign_keys_finalize_kernel");
+  }
   return VQB200_OK;
 }
 

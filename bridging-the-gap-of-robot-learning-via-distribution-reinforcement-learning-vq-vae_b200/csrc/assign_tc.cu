@@ -35,7 +35,7 @@ namespace vqb200 {
 
 int launch_assign_simt(const ZView& z, const float* E, const float* ee, int K, int D,
                        int32_t* idx, float* best, const int32_t* row_list, const int32_t* row_count,
-                       long long max_rows, cudaStream_t stream);
+                       long long max_rows, cudaStream_t stream, unsigned long long* keys = nullptr);
 
 namespace tc {
 using namespace tcc;
@@ -391,8 +391,14 @@ bool assign_tc_eligible(const ZView& z, int K, int D) {
   return D == tc::D && z.C == tc::D && K >= 1 && z.N >= 1;
 }
 
-// workspace: [0] int32 list_count, [1] int32 error word, [64 ..) int32 row list (N entries)
-size_t assign_tc_workspace_bytes(long long N) { return 256 + (size_t)(N > 0 ? N : 0) * sizeof(int32_t); }
+// workspace: [0] int32 list_count, [1] int32 error word, [64 ..) int32 row list (N entries); for N <= SPLIT_MAX_ROWS
+// additionally N 64-bit merge keys (8-byte aligned) so that the exact kernel can split short work lists over codes
+constexpr long long SPLIT_MAX_ROWS = 262144;
+static size_t tc_keys_offset(long long N) { return (256 + (size_t)(N > 0 ? N : 0) * sizeof(int32_t) + 7) & ~(size_t)7; }
+size_t assign_tc_workspace_bytes(long long N) {
+  const size_t base = 256 + (size_t)(N > 0 ? N : 0) * sizeof(int32_t);
+  return (N > 0 && N <= SPLIT_MAX_ROWS) ? tc_keys_offset(N) + (size_t)N * sizeof(unsigned long long) : base;
+}
 
 bool assign_tc_can_fuse_residual(const ZView& z, const float* r_out) {
   const bool aligned = ((reinterpret_cast<uintptr_t>(z.p) | reinterpret_cast<uintptr_t>(r_out)) & 15) == 0;
@@ -446,12 +452,14 @@ int launch_assign_tc(const ZView& z, const float* E, const float* ee, const void
   vq_assign_tc_kernel<<<grid, NTHREADS, SMEM_TOTAL, stream>>>(p);
   VQ_LAUNCH_CHECK("vq_assign_tc_kernel");
   // exact re-do of the rows the filter could not prove (count lives on the device; no host sync)
+  unsigned long long* keys = (z.N <= SPLIT_MAX_ROWS)
+      ? reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(workspace) + tc_keys_offset(z.N)) : nullptr;
   if (r_out) {
     VQ_CHECK_ARG(p.stage_mode != STG_DIRECT, VQB200_EUNSUPPORTED, "vq_assign(TC): fused residual needs a contiguous layout");
     ZView zr = z; zr.p = r_out;                    // the rows that were quantized are the NEW residual
-    return launch_assign_simt(zr, E, ee, K, D, idx, best, p.list, p.list_count, z.N, stream);
+    return launch_assign_simt(zr, E, ee, K, D, idx, best, p.list, p.list_count, z.N, stream, keys);
   }
-  return launch_assign_simt(z, E, ee, K, D, idx, best, p.list, p.list_count, z.N, stream);
+  return launch_assign_simt(z, E, ee, K, D, idx, best, p.list, p.list_count, z.N, stream, keys);
 }
 
 }  // namespace vqb200

@@ -19,7 +19,7 @@ namespace vqb200 {
 
 int launch_assign_simt(const ZView& z, const float* E, const float* ee, int K, int D,
                        int32_t* idx, float* best, const int32_t* row_list, const int32_t* row_count,
-                       long long max_rows, cudaStream_t stream);
+                       long long max_rows, cudaStream_t stream, unsigned long long* keys = nullptr);
 
 namespace tcg {
 using namespace tcc;

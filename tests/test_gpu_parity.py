@@ -616,6 +616,32 @@ def test_nan_and_tie_rules():
     np.testing.assert_array_equal(N_(mod.last_indices), ref["indices"])
 
 
+def test_short_work_list_split_merge_keeps_nan_and_tie_rules():
+    """Mid-size N: the unproven rows of the tensor-core path are re-done by the exact kernel with the codebook sweep
+    split over several CTAs and merged through 64-bit atomicMin keys; the merge must keep torch.argmin's rules
+    (first minimum, a NaN distance wins) -- compare with the unsplit exact kernel on crafted rows."""
+    vq = _mods()
+    from vqb200 import _lib
+    torch.manual_seed(9)
+    K, D, B, Tt = 1024, 64, 500, 10
+    w = 0.3 * torch.randn(K, D, device=DEV)
+    w[700] = w[3]; w[901] = w[3]; w[512] = w[130]          # duplicate codes: exact ties across different splits
+    z = 0.5 * torch.randn(B, D, Tt, device=DEV)
+    zt = z.permute(0, 2, 1)                                # [B,T,D] view of the same storage
+    zt[0, 0] = w[3]; zt[1, 1] = w[901]; zt[2, 2] = w[512]  # rows that ARE duplicated codes
+    zt[3, 3, 5] = float("nan"); zt[4, 4] = float("inf"); zt[5, 5] = 0.0
+    zt[6, 6] = 0.5 * (w[10] + w[20])                       # near-tie between two codes
+    st = vq.QuantizerState(K, D, torch.device(DEV))
+    exact = vq.vq_assign(z, w, st, _lib.ASSIGN_SIMT)
+    auto = vq.vq_assign(z, w, st, _lib.ASSIGN_AUTO)
+    assert torch.equal(exact, auto)
+    assert int(auto[0, 0]) == 3 and int(auto[1, 1]) == 3 and int(auto[2, 2]) == 130
+    # every row unproven (all-equal codebook): the whole batch goes through the split merge
+    w2 = w[:1].expand(K, D).contiguous()
+    st2 = vq.QuantizerState(K, D, torch.device(DEV))
+    assert int(vq.vq_assign(z, w2, st2, _lib.ASSIGN_AUTO).abs().max()) == 0
+
+
 def test_called_twice_per_step_like_student_mode():
     """The shared quantizer is invoked twice per forward (robot + human branch) and the EMA state
     mutates between the calls; backward of the first call must use ITS codebook."""
