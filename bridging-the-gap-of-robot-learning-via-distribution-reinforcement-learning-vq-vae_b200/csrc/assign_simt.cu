@@ -25,20 +25,6 @@ constexpr int LDZ = BM + 4;
 constexpr int LDE = BN + 4;
 }  // namespace simt
 
-// (distance, index) -> 64-bit key whose unsigned order is the cand_better order: NaN first, then ascending
-// distance (-0 == +0), ties by ascending index.
-__device__ __forceinline__ unsigned long long cand_key(float d, int i) {
-  unsigned u;
-  if (d != d) u = 0u;
-  else {
-    if (d == 0.f) d = 0.f;
-    u = __float_as_uint(d);
-    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-    if (u == 0u) u = 1u;                           // keep 0 for NaN only (-NaN bit patterns never reach here)
-  }
-  return ((unsigned long long)u << 32) | (unsigned)i;
-}
-
 __global__ void __launch_bounds__(256)
 assign_keys_finalize_kernel(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ row_list,
                             const int32_t* __restrict__ row_count, int32_t* __restrict__ idx_out) {

@@ -114,6 +114,20 @@ __device__ __forceinline__ bool cand_better(float da, int ia, float db, int ib) 
   return dist_less(da, db) || (dist_same(da, db) && ia < ib);
 }
 
+// (distance, index) -> 64-bit key whose unsigned order is the cand_better order: NaN first, then ascending
+// distance (-0 == +0), ties by ascending index.
+__device__ __forceinline__ unsigned long long cand_key(float d, int i) {
+  unsigned u;
+  if (d != d) u = 0u;
+  else {
+    if (d == 0.f) d = 0.f;
+    u = __float_as_uint(d);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    if (u == 0u) u = 1u;                           // keep 0 for NaN only (-NaN bit patterns never reach here)
+  }
+  return ((unsigned long long)u << 32) | (unsigned)i;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -10,6 +10,7 @@
 // (d = fl(fl(|x|^2 + |E|^2) - 2 x.E), first minimum, NaN wins) and of ema.cu / gather.cu.
 // Eligible: D == 64, N <= 4096, K <= 4096, S <= 8, single process (no inter-GPU all-reduce inside the launch).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -333,6 +334,345 @@ rvq_small_kernel(const Args a) {
 }
 
 }  // namespace small
+
+// ==========================================================================================
+// Wide variant (the BASELINE cfg2 shape and its neighbours: N <= 1024, S * K <= 3072): the same algorithm spread
+// over the whole GPU instead of one GPC.  Grid = 16 row blocks x 8 code slices = 128 CTAs; the 8 CTAs that share a
+// row block form a cluster.  What makes it fast is the dependency chain, not the FLOPs:
+//   * every CTA loads its code slice of EVERY stage (pre-update codebooks, known at launch) once, up front;
+//   * per stage: partial argmin over the slice -> ONE cluster barrier, candidates merged through distributed shared
+//     memory (64-bit keys, cand_better order) -> EMA statistics as L2 reductions -> ONE grid barrier -> every CTA
+//     derives cs', n and the updated codewords of its rows' codes locally (same formulas, same bits as the in-place
+//     update) and applies gather / residual / running sum to its private copy of the row block;
+//   * the in-place update of (ema_cluster_size, ema_w, embedding) of stage s is deferred until the next grid barrier
+//     has proven that nobody reads the old values any more.
+// The grid barrier is a monotonically increasing counter in the workspace with a bounded spin (a protocol bug traps
+// instead of hanging the GPU); the launch is cooperative, so all 128 CTAs are co-resident.
+// ==========================================================================================
+namespace wide {
+using small::Args;
+using small::stats_offset;
+constexpr int D = 64, NT = 256, CS = 8, MAX_RB = 16;    // code slices (cluster size), row blocks (runtime: as many 8-CTA
+                                                        // clusters as the device can keep co-resident, at most 16)
+constexpr int MAX_RPB = 64;                             // rows per block  (N <= 1024)
+constexpr int MAX_SLICE_CODES = 384;                    // sum over stages of ceil(K_s / 8)  (S*K <= 3072)
+constexpr int LDR = D + 1;
+constexpr unsigned SPIN_LIMIT = 1u << 24;
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& generation, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const unsigned target = (generation + 1u) * nblocks;
+    unsigned spins = 0;
+    while (true) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= target) break;
+      if (++spins > SPIN_LIMIT) __trap();
+    }
+    __threadfence();
+  }
+  ++generation;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT, 1)
+rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) float smem[];
+  float* R = smem;                                  // [MAX_RPB][LDR] running residual (private copy of the row block)
+  float* O = R + MAX_RPB * LDR;                     // [MAX_RPB][LDR] running sum of the straight-through values
+  float* Es = O + MAX_RPB * LDR;                    // [MAX_SLICE_CODES][D] this CTA's code slice of every stage
+  float* ees = Es + MAX_SLICE_CODES * D;            // [MAX_SLICE_CODES] |E_k|^2
+  float* csn = ees + MAX_SLICE_CODES;               // [MAX_K] cs' of the current stage
+  float* bestd = csn + small::MAX_K;                // [8 warps][32]
+  int* bestk = reinterpret_cast<int*>(bestd + 8 * 32);
+  int* rowk = bestk + 8 * 32;                       // [MAX_RPB]
+  unsigned long long* ckey = reinterpret_cast<unsigned long long*>(rowk + MAX_RPB);   // [MAX_RPB] this slice's candidates
+  __shared__ double red[8];
+  __shared__ float s_n;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slice = (int)cluster.block_rank();      // code slice 0..7
+  const int rb = blockIdx.x / CS;                   // row block 0..15
+  const unsigned nblocks = gridDim.x;
+  const int cta = blockIdx.x;
+  unsigned generation = 0;
+  const long long N = a.z.N;
+  const int RB = (int)(gridDim.x / CS);
+  const int rpb = (int)((N + RB - 1) / RB);
+  const long long row0 = (long long)rb * rpb;
+  const int rows = (int)max(0LL, min((long long)rpb, N - row0));
+  const int C = (int)a.z.C, T = (int)a.z.T;
+
+  // ---- prologue: rows, and this CTA's slice of every stage's (pre-update) codebook with |E|^2 ----
+  for (int i = tid; i < rows * D; i += NT) {
+    const int r = i / D, k = i - r * D;
+    R[r * LDR + k] = __ldg(a.z.p + a.z.row_base(row0 + r) + (long long)k * a.z.sC);
+    O[r * LDR + k] = 0.f;
+  }
+  int sl_off[small::MAX_S + 1];                     // slice offsets (codes) inside Es per stage
+  sl_off[0] = 0;
+#pragma unroll
+  for (int s = 0; s < small::MAX_S; ++s) sl_off[s + 1] = sl_off[s] + (s < a.S ? (a.K[s] + CS - 1) / CS : 0);
+  for (int s = 0; s < a.S; ++s) {
+    const int per = (a.K[s] + CS - 1) / CS;
+    const int k0 = min(a.K[s], slice * per), k1 = min(a.K[s], k0 + per);
+    const float4* src = reinterpret_cast<const float4*>(a.E[s] + (size_t)k0 * D);
+    float4* dst = reinterpret_cast<float4*>(Es + (size_t)sl_off[s] * D);
+    for (int i = tid; i < (k1 - k0) * (D / 4); i += NT) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  for (int s = 0; s < a.S; ++s) {
+    const int per = (a.K[s] + CS - 1) / CS;
+    const int k0 = min(a.K[s], slice * per), k1 = min(a.K[s], k0 + per);
+    for (int k = tid; k < k1 - k0; k += NT) {
+      const float4* e4 = reinterpret_cast<const float4*>(Es + (size_t)(sl_off[s] + k) * D);
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < D / 4; ++c) {             // same summation order as the narrow kernel / codebook_prepare
+        const float4 v = e4[(c + lane) & (D / 4 - 1)];
+        acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+      }
+      ees[sl_off[s] + k] = acc;
+    }
+  }
+  __syncthreads();
+
+  // in-place EMA update of one stage, this CTA's share of the codes (all 128 CTAs split the codebook)
+  auto update_stage = [&](int sp, float n) {
+    const int Kp = a.K[sp];
+    const float* dwp = a.stats + stats_offset(a, sp);
+    const float* cntp = dwp + (long long)Kp * D;
+    float* csp = a.cs[sp]; float* wv = a.w[sp]; float* Ep = a.E[sp];
+    const int per = (Kp + (int)nblocks - 1) / (int)nblocks;
+    const int k0 = min(Kp, cta * per), k1 = min(Kp, k0 + per);
+    for (int i = tid; i < (k1 - k0) * (D / 4); i += NT) {
+      const int k = k0 + i / (D / 4);
+      const float csv = fmaf(__ldcg(cntp + k), a.one_minus_decay, __fmul_rn(__ldcg(csp + k), a.decay));
+      const float cl = __fmul_rn(__fdiv_rn(__fadd_rn(csv, a.eps), __fadd_rn(n, a.k_eps[sp])), n);
+      const size_t q = (size_t)k0 * (D / 4) + i;
+      const float4 d0 = __ldcg(reinterpret_cast<const float4*>(dwp) + q);
+      const float4 w0 = __ldcg(reinterpret_cast<const float4*>(wv) + q);
+      float4 n0;
+      n0.x = fmaf(d0.x, a.one_minus_decay, __fmul_rn(w0.x, a.decay)); n0.y = fmaf(d0.y, a.one_minus_decay, __fmul_rn(w0.y, a.decay));
+      n0.z = fmaf(d0.z, a.one_minus_decay, __fmul_rn(w0.z, a.decay)); n0.w = fmaf(d0.w, a.one_minus_decay, __fmul_rn(w0.w, a.decay));
+      reinterpret_cast<float4*>(wv)[q] = n0;
+      reinterpret_cast<float4*>(Ep)[q] = make_float4(__fdiv_rn(n0.x, cl), __fdiv_rn(n0.y, cl), __fdiv_rn(n0.z, cl), __fdiv_rn(n0.w, cl));
+    }
+    __syncthreads();                                  // every thread has read the old cs of the slice
+    for (int k = k0 + tid; k < k1; k += NT)
+      csp[k] = fmaf(__ldcg(cntp + k), a.one_minus_decay, __fmul_rn(__ldcg(csp + k), a.decay));
+  };
+  float n_prev = 0.f;
+
+  for (int s = 0; s < a.S; ++s) {
+    const int K = a.K[s];
+    float* dw = a.stats + stats_offset(a, s);
+    float* cnt = dw + (long long)K * D;
+    const int per = (K + CS - 1) / CS;
+    const int k0s = min(K, slice * per), ks = min(K, k0s + per) - k0s;      // this CTA's codes [k0s, k0s + ks)
+    const float* Esl = Es + (size_t)sl_off[s] * D;
+    const float* eesl = ees + sl_off[s];
+
+    // ---- K1: exact fp32 distances + argmin over this CTA's code slice (lane = row, 64 registers) ----
+    {
+      const int nb = (rows + 31) >> 5;                // 1 or 2 sub-blocks of 32 rows
+      const int G = nb <= 1 ? 8 : 4;                  // warps per sub-block
+      const int blk = warp / G, sub = warp % G;
+      const int r = blk * 32 + lane;
+      const bool valid = blk < nb && r < rows;
+      float x[D];
+      float xx = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) { x[c] = valid ? R[r * LDR + c] : 0.f; xx = fmaf(x[c], x[c], xx); }
+      float bd = INFINITY; int bk = INT_MAX;
+      if (blk < nb) {
+        for (int kk = sub; kk < ks; kk += 4 * G) {
+          const float4* e0 = reinterpret_cast<const float4*>(Esl + kk * D);       // warp-uniform: broadcast
+          const float4* e1 = reinterpret_cast<const float4*>(Esl + min(kk + G, ks - 1) * D);
+          const float4* e2 = reinterpret_cast<const float4*>(Esl + min(kk + 2 * G, ks - 1) * D);
+          const float4* e3 = reinterpret_cast<const float4*>(Esl + min(kk + 3 * G, ks - 1) * D);
+          float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+          for (int c = 0; c < D / 4; ++c) {
+            const float4 v0 = e0[c], v1 = e1[c], v2 = e2[c], v3 = e3[c];
+            d0 = fmaf(x[4 * c], v0.x, d0); d1 = fmaf(x[4 * c], v1.x, d1); d2 = fmaf(x[4 * c], v2.x, d2); d3 = fmaf(x[4 * c], v3.x, d3);
+            d0 = fmaf(x[4 * c + 1], v0.y, d0); d1 = fmaf(x[4 * c + 1], v1.y, d1); d2 = fmaf(x[4 * c + 1], v2.y, d2); d3 = fmaf(x[4 * c + 1], v3.y, d3);
+            d0 = fmaf(x[4 * c + 2], v0.z, d0); d1 = fmaf(x[4 * c + 2], v1.z, d1); d2 = fmaf(x[4 * c + 2], v2.z, d2); d3 = fmaf(x[4 * c + 2], v3.z, d3);
+            d0 = fmaf(x[4 * c + 3], v0.w, d0); d1 = fmaf(x[4 * c + 3], v1.w, d1); d2 = fmaf(x[4 * c + 3], v2.w, d2); d3 = fmaf(x[4 * c + 3], v3.w, d3);
+          }
+          const float dots[4] = {d0, d1, d2, d3};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int kl = kk + u * G;
+            if (kl < ks) {
+              const int k = k0s + kl;
+              const float dd = __fsub_rn(__fadd_rn(xx, eesl[kl]), __fmul_rn(2.0f, dots[u]));
+              if (cand_better(dd, k, bd, bk)) { bd = dd; bk = k; }
+            }
+          }
+        }
+      }
+      bestd[warp * 32 + lane] = bd; bestk[warp * 32 + lane] = bk;
+      __syncthreads();
+      if (sub == 0 && valid) {
+        for (int g2 = 1; g2 < G; ++g2) {
+          const float od = bestd[(warp + g2) * 32 + lane]; const int ok = bestk[(warp + g2) * 32 + lane];
+          if (cand_better(od, ok, bd, bk)) { bd = od; bk = ok; }
+        }
+        ckey[r] = cand_key(bd, bk);
+      }
+    }
+    cluster.sync();                                   // all 8 slices of this row block have their candidates
+    for (int r = tid; r < rows; r += NT) {
+      unsigned long long best = ~0ull;
+#pragma unroll
+      for (int c = 0; c < CS; ++c) {
+        const unsigned long long v = cluster.map_shared_rank(ckey, c)[r];
+        best = v < best ? v : best;
+      }
+      rowk[r] = (int)(best & 0xFFFFFFFFull);
+    }
+    __syncthreads();
+
+    // ---- statistics (the row block's rows are dealt round-robin to the 8 CTAs of the cluster) ----
+    for (int r = slice + CS * (tid / (D / 4)); r < rows; r += CS * (NT / (D / 4))) {
+      const int q = tid % (D / 4);
+      const int k = rowk[r];
+      if (q == 0) { atomicAdd(cnt + k, 1.0f); a.idx[(long long)s * N + row0 + r] = k; }
+      if (a.training_ema) {
+        const float* p = R + r * LDR + 4 * q;
+        red_add_v4(dw + (size_t)k * D + 4 * q, p[0], p[1], p[2], p[3]);
+      }
+    }
+
+    float n_stage = 0.f;
+    if (a.training_ema) {
+      grid_barrier(barrier, generation, nblocks);     // the statistics of stage s are complete (also orders ckey reuse)
+      if (s > 0) update_stage(s - 1, n_prev);         // nobody reads stage s-1's old state any more
+      {
+        const float* cs = a.cs[s];
+        double part = 0.0;
+        for (int k = tid; k < K; k += NT) {
+          const float v = fmaf(__ldcg(cnt + k), a.one_minus_decay, __fmul_rn(__ldcg(cs + k), a.decay));
+          csn[k] = v;
+          part += (double)v;
+        }
+        part = warp_sum(part);
+        if (lane == 0) red[warp] = part;
+        __syncthreads();
+        if (tid < 32) {
+          double v = tid < 8 ? red[tid] : 0.0;
+          v = warp_sum(v);
+          if (tid == 0) s_n = (float)v;
+        }
+        __syncthreads();
+        n_stage = s_n;
+      }
+    } else {
+      cluster.sync();                                 // eval / standard VQ: only ckey reuse needs ordering
+    }
+
+    // ---- gather (post-update codeword), straight-through value, loss sum, running sum, next residual ----
+    float part = 0.f;
+    {
+      constexpr int U = 4;
+      const float* Eg = a.E[s];
+      for (int i0 = tid; i0 < rows * D; i0 += NT * U) {
+        float q[U]; int ri[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * NT;
+          if (i < rows * D) {
+            const int r = i / D, c = i - r * D;
+            ri[u] = r * LDR + c;
+            const int k = rowk[r];
+            if (a.training_ema) {
+              const float cl = __fmul_rn(__fdiv_rn(__fadd_rn(csn[k], a.eps), __fadd_rn(n_stage, a.k_eps[s])), n_stage);
+              const float wn = fmaf(__ldcg(dw + (size_t)k * D + c), a.one_minus_decay,
+                                    __fmul_rn(__ldcg(a.w[s] + (size_t)k * D + c), a.decay));
+              q[u] = __fdiv_rn(wn, cl);
+            } else {
+              q[u] = __ldcg(Eg + (size_t)k * D + c);
+            }
+          } else { ri[u] = -1; q[u] = 0.f; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (ri[u] < 0) continue;
+          const float x = R[ri[u]];
+          const float diff = __fsub_rn(q[u], x);
+          const float st = __fadd_rn(x, diff);
+          part = fmaf(diff, diff, part);
+          O[ri[u]] = __fadd_rn(O[ri[u]], st);
+          R[ri[u]] = __fsub_rn(x, st);
+        }
+      }
+    }
+    {
+      double p = warp_sum((double)part);
+      __syncthreads();
+      if (lane == 0) red[warp] = p;
+      __syncthreads();
+      if (tid < 32 && slice == 0) {                   // every slice computed the same sum: one of them reports it
+        double v = tid < 8 ? red[tid] : 0.0;
+        v = warp_sum(v);
+        if (tid == 0 && v != 0.0) atomicAdd(a.sse + s, v);
+      }
+    }
+    __syncthreads();
+    n_prev = n_stage;
+  }
+
+  // ---- output: the row block's rows are dealt to the 8 CTAs of the cluster ----
+  for (int i = tid; i < rows * D; i += NT) {
+    const int r = i / D, c = i - r * D;
+    if ((r & (CS - 1)) != slice) continue;
+    const long long n = row0 + r;
+    const long long b = n / T; const int t = (int)(n - b * T);
+    a.out[(b * C + c) * T + t] = O[r * LDR + c];
+  }
+  grid_barrier(barrier, generation, nblocks);
+  if (a.training_ema) update_stage(a.S - 1, n_prev);
+
+  // ---- loss / perplexity / dcr of every stage (CTA 0, one warp per stage) ----
+  if (cta == 0 && warp < a.S) {
+    const int s = warp;
+    const int K = a.K[s];
+    const float* cnt = a.stats + stats_offset(a, s) + (long long)K * D;
+    const float Nf = (float)N;
+    double ent = 0.0; int active = 0;
+    for (int k0 = 0; k0 < K; k0 += 32 * 8) {
+      float c8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int k = k0 + u * 32 + lane; c8[u] = (k < K) ? __ldcg(cnt + k) : 0.f; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float p = __fdiv_rn(c8[u], Nf);
+        ent += (double)__fmul_rn(p, logf(__fadd_rn(p, 1e-10f)));
+        active += (c8[u] > 0.f);
+      }
+    }
+    ent = warp_sum(ent);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) active += __shfl_xor_sync(0xffffffffu, active, o);
+    if (lane == 0) {
+      const float mse = (float)(__ldcg(a.sse + s) / ((double)N * D));
+      a.m3[s * 3 + 0] = a.use_ema ? __fmul_rn(a.commitment, mse) : __fadd_rn(mse, __fmul_rn(a.commitment, mse));
+      a.m3[s * 3 + 1] = expf(-(float)ent);
+      a.m3[s * 3 + 2] = __fsub_rn(1.0f, __fdiv_rn((float)active, (float)K));
+    }
+  }
+  cluster.sync();                                     // no CTA exits while its shared memory may still be read
+}
+
+constexpr size_t SMEM_BYTES = ((size_t)2 * MAX_RPB * LDR + (size_t)MAX_SLICE_CODES * (D + 1) + small::MAX_K + 8 * 32) * sizeof(float) +
+                              (8 * 32 + MAX_RPB) * sizeof(int) + MAX_RPB * sizeof(unsigned long long) + 16;
+
+}  // namespace wide
 }  // namespace vqb200
 
 using namespace vqb200;
@@ -383,6 +723,55 @@ int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, in
   a.stats = workspace;
   a.scratch = workspace + ((stats_floats + 3) & ~(size_t)3);
   a.sse = sse; a.idx = idx; a.out = out; a.m3 = m3;
+
+  // ---- wide variant: the whole GPU instead of one GPC (see namespace wide) ----
+  {
+    long long slice_codes = 0;
+    for (int s = 0; s < S; ++s) slice_codes += (K[s] + wide::CS - 1) / wide::CS;
+    static const int wide_off = [] { const char* e = getenv("VQB200_RVQ_SMALL_NARROW"); return e ? atoi(e) : 0; }();
+    static thread_local int coop = -1;
+    if (coop < 0) {
+      int dev = 0, v = 0;
+      coop = (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && v) ? 1 : 0;
+    }
+    static thread_local int max_rb = -1;             // co-resident 8-CTA clusters (GPC floor-planning decides, not SMs / 8)
+    if (coop == 1 && max_rb < 0) {
+      VQ_CUDA(cudaFuncSetAttribute(wide::rvq_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide::SMEM_BYTES));
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(wide::MAX_RB * wide::CS); q.blockDim = dim3(wide::NT); q.dynamicSmemBytes = wide::SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = wide::CS; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, wide::rvq_wide_kernel, &q) != cudaSuccess) { cudaGetLastError(); nc = 0; }
+      max_rb = nc > wide::MAX_RB ? wide::MAX_RB : nc;
+    }
+    if (!wide_off && coop == 1 && max_rb >= 4 && B * T <= (long long)max_rb * wide::MAX_RPB &&
+        slice_codes <= wide::MAX_SLICE_CODES) {
+      const int rb_used = (int)std::min<long long>(max_rb, (B * T + 15) / 16);            // at least 16 rows per block
+      size_t scratch_floats = 0;
+      for (int s = 0; s < S; ++s) scratch_floats += (size_t)K[s] + 8;
+      unsigned* barrier = reinterpret_cast<unsigned*>(a.scratch + scratch_floats);       // inside the +16 slack
+      const size_t zero_bytes = (size_t)((reinterpret_cast<unsigned char*>(barrier) + 16) - reinterpret_cast<unsigned char*>(workspace));
+      VQ_CUDA(cudaMemsetAsync(workspace, 0, zero_bytes, stream));                        // statistics + barrier counter
+      VQ_CUDA(cudaMemsetAsync(sse, 0, (size_t)S * sizeof(double), stream));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((rb_used < 1 ? 1 : rb_used) * wide::CS);
+      cfg.blockDim = dim3(wide::NT);
+      cfg.dynamicSmemBytes = wide::SMEM_BYTES;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = wide::CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeCooperative;
+      attr[1].val.cooperative = 1;
+      cfg.attrs = attr; cfg.numAttrs = 2;
+      VQ_CUDA(cudaLaunchKernelEx(&cfg, wide::rvq_wide_kernel, a, barrier));
+      VQ_LAUNCH_CHECK("rvq_wide_kernel");
+      return VQB200_OK;
+    }
+  }
 
   const size_t smem = ((size_t)MAX_ROWS_PER_CTA * LDR + MAX_K + 8 * 32 + (size_t)CHUNK * D) * sizeof(float) +
                       (8 * 32 + MAX_ROWS_PER_CTA) * sizeof(int);

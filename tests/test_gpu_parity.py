@@ -367,6 +367,37 @@ def test_cfg3_rvq_chunk():
         print("cfg3 chunk step", step, "benign flips", flips)
 
 
+@pytest.mark.parametrize("B,Tt,S,K,training", [(7, 1, 4, 512, True), (100, 3, 4, 512, True), (512, 1, 4, 512, True),
+                                                 (1000, 1, 3, 700, True), (1024, 1, 2, 1024, True),
+                                                 (1025, 1, 4, 512, True), (300, 10, 4, 512, True),
+                                                 (512, 1, 4, 512, False), (97, 2, 8, 333, True)])
+def test_single_launch_rvq_shapes(B, Tt, S, K, training):
+    """K4 (rvq_small.cu) on both of its kernels: the whole-GPU cooperative variant (N <= 1024, S*K <= 3072) and the
+    one-cluster variant (larger N / more codes), two steps each against the oracle, plus the multi-kernel path on the
+    same state (indices must be identical: all three are exact fp32 with the same summation order)."""
+    vq = _mods()
+    D = 64
+    mod = vq.ResidualVQ(S, K, D, use_ema=True).to(DEV)
+    twin = vq.ResidualVQ(S, K, D, use_ema=True).to(DEV)
+    for l in twin.layers:
+        l.assign_algo = vq._lib.ASSIGN_SIMT          # forces the multi-kernel path
+    stages = [_fresh_state(K, D, True, 300 + s, "small") for s in range(S)]
+    for l, l2, st in zip(mod.layers, twin.layers, stages):
+        _load_vq(l, st)
+        _load_vq(l2, st)
+    rng = np.random.default_rng(77 + B)
+    for step in range(2):
+        z = (0.5 * rng.standard_normal((B, D, Tt))).astype(np.float32)
+        g = rng.standard_normal((B, D, Tt)).astype(np.float32)
+        twin.train(training)
+        with torch.no_grad():
+            twin(T(z))
+        _rvq_step(mod, stages, z, g, 1.0, training)
+        np.testing.assert_array_equal(N_(mod.last_indices), N_(twin.last_indices))
+        for l, l2 in zip(mod.layers, twin.layers):
+            assert_close(N_(l.embedding.weight), N_(l2.embedding.weight), TOL, "E single-launch vs multi-kernel", rows=True)
+
+
 def _proj_oracle_grads(z, z_q, g, g_ze, w_in, w_out):
     """Autograd of out = W_out z_q + b_out, z_e = W_in z + b_in with straight-through z_q (float64)."""
     z, z_q, g, g_ze = (np.asarray(a, np.float64) for a in (z, z_q, g, g_ze))
