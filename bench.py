@@ -186,7 +186,7 @@ def run_gpu(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-        vqb200.dist.enable()
+        vqb200.dist.enable(peer=args.exchange)
     cfg = dict(WORKLOADS[args.workload])
     if args.windows:
         cfg["B"] = args.windows
@@ -366,9 +366,10 @@ def run_gpu(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: ResidualVQ S={S} K={K} D={D} EMA training step (fwd+EMA+bwd), "
                                f"z [{B},{D},{T}] fp32 per GPU = {N} vectors/GPU, batch sharded on dim 0, per-stage "
-                               f"EMA stats all-reduced (NCCL)" if cfg["kind"] == "rvq" else
+                               f"EMA stats summed across ranks" if cfg["kind"] == "rvq" else
                                f"{args.workload}: VectorQuantizer K={K} D={D} EMA training step, z [{B},{D},{T}] per GPU",
                    "vectors_per_gpu": N, "parallelism": f"dp{world}",
+                   "stats_exchange": vqb200.dist.peer_status() if world > 1 else "none (single GPU)",
                    "l2": "inputs larger than L2 (2.56 GB per tensor per GPU)" if N * D * 4 > 256e6 else "L2 not flushed (small input)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roof, "cpu_baseline": cpu,
@@ -520,6 +521,9 @@ def main():
     ap.add_argument("--impl", default="vqb200", choices=["vqb200", "reference"])
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
     ap.add_argument("--windows", type=int, default=0, help="override the number of windows B (development only)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="transport of the per-stage EMA statistics at N > 1: peer memory fused into the finalize "
+                         "kernels (csrc/peer.cu) or an NCCL all-reduce; auto = peer when the node allows it")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()

@@ -29,6 +29,13 @@ _SIGNATURES = {
     "vqb200_ema_accumulate": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                       _P, _P, c_int64, _P, c_int, _P]),
     "vqb200_ema_finalize": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_double, c_double, _P, _P, _P, _P, _P]),
+    "vqb200_peer_alloc": (c_int, [c_size_t, _P, _P]),
+    "vqb200_peer_open": (c_int, [_P, _P]),
+    "vqb200_peer_close": (c_int, [_P]),
+    "vqb200_peer_free": (c_int, [_P]),
+    "vqb200_peer_barrier": (c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32, _P]),
+    "vqb200_ema_finalize_peer": (c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32, _P, _P, _P, _P,
+                                         c_int64, c_int64, c_double, c_double, _P, _P, _P, _P, _P]),
     "vqb200_vq_histogram": (c_int, [_P, c_int64, c_int64, _P, _P]),
     "vqb200_vq_gather_st": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                     _P, _P, c_int64, _P, _P, _P, c_int, _P, _P]),

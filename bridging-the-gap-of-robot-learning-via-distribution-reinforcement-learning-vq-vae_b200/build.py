@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libvqb200.so")
-SOURCES = ["abi.cu", "assign.cu", "assign_simt.cu", "assign_tc.cu", "assign_tc_gen.cu", "ema.cu", "gather.cu", "tile_ops.cu", "rvq_small.cu", "fsq_lfq.cu", "fsq_lfq_fused.cu", "tokens.cu"]
+SOURCES = ["abi.cu", "assign.cu", "assign_simt.cu", "assign_tc.cu", "assign_tc_gen.cu", "ema.cu", "peer.cu", "gather.cu", "tile_ops.cu", "rvq_small.cu", "fsq_lfq.cu", "fsq_lfq_fused.cu", "tokens.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2", "--use_fast_math=false"]
 

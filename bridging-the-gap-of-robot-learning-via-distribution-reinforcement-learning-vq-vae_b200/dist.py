@@ -8,11 +8,23 @@ The only coupled quantities of the path are linear sums over vectors (SURVEY.md 
     result instead);
   * gradients of the small encoder/decoder and of a standard-VQ codebook: averaged (DDP semantics).
 
-Everything here works on CPU tensors with the `gloo` backend as well, which is how the host-side
-logic is tested without a GPU (tests/test_dist_gloo.py).
+Transport of the per-stage exchange, chosen by `enable(peer=...)`:
+  * "nccl" -- `all_reduce(stats)` between K3a and K3b (NCCL over NVLink / NVSwitch);
+  * "peer" -- no collective launch at all: K3a accumulates into a CUDA-IPC symmetric buffer and the finalize
+    kernels barrier + read every rank's slot over NVLink themselves, summing in rank order
+    (csrc/peer.cu, `vqb200_ema_finalize_peer`); bit-identical codebooks on all ranks;
+  * "auto" (default) -- "peer" when every rank of the group sits on the same host, owns a distinct CUDA device and
+    the IPC mapping plus a handshake barrier succeed on ALL ranks; otherwise "nccl" (reason kept in
+    `peer_status()`).
+
+Everything except the peer transport works on CPU tensors with the `gloo` backend as well, which is how the
+host-side logic is tested without a GPU (tests/test_dist_gloo.py).
 """
 from __future__ import annotations
 
+import ctypes
+import os
+import socket
 from typing import Iterable, List, Optional, Tuple
 
 import torch
@@ -20,20 +32,173 @@ import torch.distributed as torch_dist
 
 _GROUP = None
 _ENABLED = False
+_PEER: Optional["PeerExchange"] = None
+_PEER_STATUS = "off"
+
+FLAG_BYTES = 256                       # VQB200_MAX_PEERS x uint32, padded
+DEFAULT_SLOT_BYTES = 16 << 20          # K*(D+1)*4 per stage: 266 KB at 1024 x 64, 8.4 MB at 16384 x 128
 
 
-def enable(group=None) -> None:
-    """Turn on the per-stage EMA-statistics all-reduce (call after init_process_group)."""
-    global _GROUP, _ENABLED
+class PeerExchange:
+    """Symmetric CUDA-IPC buffer `[flags | slot 0 | slot 1]` mapped by every rank of one node, plus the epoch /
+    slot bookkeeping of `vqb200_ema_finalize_peer` (include/vqb200.h).  Construction is collective."""
+
+    def __init__(self, group, device: torch.device, slot_bytes: int = DEFAULT_SLOT_BYTES):
+        from . import _lib
+        lib = _lib.load()
+        self.lib = lib
+        self.group = group
+        self.device = torch.device(device)
+        self.rank = torch_dist.get_rank(group)
+        self.world = torch_dist.get_world_size(group)
+        self.slot_bytes = (int(slot_bytes) + 255) // 256 * 256
+        self.epoch = 0
+        self.base: List[int] = [0] * self.world
+        self._opened: List[int] = []
+        self._own = 0
+        if self.world > 16:
+            raise RuntimeError("peer exchange supports at most 16 ranks of one node")
+        total = FLAG_BYTES + 2 * self.slot_bytes
+        handle = (ctypes.c_ubyte * 64)()
+        own = ctypes.c_void_p()
+        err = ""
+        with torch.cuda.device(self.device):
+            rc = lib.vqb200_peer_alloc(ctypes.c_size_t(total), ctypes.byref(own), handle)
+            if rc != 0:
+                err = f"peer_alloc rc={rc}: {_lib.last_error()}"
+            else:
+                self._own = int(own.value)
+        me = {"host": socket.gethostname(), "pid": os.getpid(), "handle": bytes(handle), "err": err,
+              "dev": _device_uuid(self.device)}
+        infos: List[Optional[dict]] = [None] * self.world
+        torch_dist.all_gather_object(infos, me, group=group)
+        if not err:
+            if any(i["err"] for i in infos):
+                err = "a peer failed to allocate: " + "; ".join(i["err"] for i in infos if i["err"])
+            elif len({i["host"] for i in infos}) != 1:
+                err = "ranks span several hosts (peer memory is intra-node)"
+            elif len({i["dev"] for i in infos}) != self.world:
+                err = "two ranks share one CUDA device"
+        if not err:
+            with torch.cuda.device(self.device):
+                for p, info in enumerate(infos):
+                    if p == self.rank:
+                        self.base[p] = self._own
+                        continue
+                    mapped = ctypes.c_void_p()
+                    rc = lib.vqb200_peer_open((ctypes.c_ubyte * 64).from_buffer_copy(info["handle"]), ctypes.byref(mapped))
+                    if rc != 0:
+                        err = f"peer_open(rank {p}) rc={rc}: {_lib.last_error()}"
+                        break
+                    self.base[p] = int(mapped.value)
+                    self._opened.append(int(mapped.value))
+        oks: List[Optional[str]] = [None] * self.world
+        torch_dist.all_gather_object(oks, err, group=group)
+        bad = [f"rank {p}: {e}" for p, e in enumerate(oks) if e]
+        if bad:
+            self.close()
+            raise RuntimeError("; ".join(bad))
+        self._flags = (ctypes.c_void_p * self.world)(*self.base)
+        self._slots = [(ctypes.c_void_p * self.world)(*[b + FLAG_BYTES + s * self.slot_bytes for b in self.base])
+                       for s in range(2)]
+        # handshake: one barrier round through the flag words proves the mapping works in both directions
+        with torch.cuda.device(self.device):
+            self.epoch += 1
+            rc = lib.vqb200_peer_barrier(self._flags, self.rank, self.world, ctypes.c_uint32(self.epoch),
+                                         ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+            if rc != 0:
+                raise RuntimeError(f"peer_barrier rc={rc}: {_lib.last_error()}")
+            torch.cuda.synchronize(self.device)
+
+    def fits(self, K: int, D: int) -> bool:
+        return K * (D + 1) * 4 <= self.slot_bytes
+
+    def next_slot(self):
+        """Advance the epoch; returns (epoch, device pointer of MY slot, table of every rank's slot)."""
+        self.epoch = (self.epoch + 1) & 0xFFFFFFFF
+        s = self.epoch & 1
+        return self.epoch, self._own + FLAG_BYTES + s * self.slot_bytes, self._slots[s]
+
+    @property
+    def flags(self):
+        return self._flags
+
+    def close(self) -> None:
+        """Collective when the process group is still alive: unmap the peers' buffers, barrier, free the own one."""
+        lib = self.lib
+        if torch.cuda.is_available():
+            torch.cuda.synchronize(self.device)
+        for m in self._opened:
+            lib.vqb200_peer_close(ctypes.c_void_p(m))
+        self._opened = []
+        try:
+            if torch_dist.is_initialized():
+                torch_dist.barrier(group=self.group)
+        except Exception:
+            pass
+        if self._own:
+            lib.vqb200_peer_free(ctypes.c_void_p(self._own))
+            self._own = 0
+
+
+def _device_uuid(device: torch.device) -> str:
+    try:
+        return str(torch.cuda.get_device_properties(device).uuid)
+    except Exception:
+        return f"{socket.gethostname()}:{device}"
+
+
+def enable(group=None, peer: str = "auto", device: Optional[torch.device] = None,
+           slot_bytes: int = DEFAULT_SLOT_BYTES) -> None:
+    """Turn on the per-stage EMA-statistics exchange (call after init_process_group; collective).
+    peer: "auto" | "peer" | "nccl" (see the module docstring).  `device` defaults to the current CUDA device."""
+    global _GROUP, _ENABLED, _PEER, _PEER_STATUS
     if not torch_dist.is_available() or not torch_dist.is_initialized():
         raise RuntimeError("vqb200.dist.enable(): torch.distributed is not initialised")
+    if peer not in ("auto", "peer", "nccl"):
+        raise ValueError("peer must be 'auto', 'peer' or 'nccl'")
+    _close_peer()
     _GROUP = group
     _ENABLED = True
+    _PEER_STATUS = "nccl (requested)" if peer == "nccl" else "nccl"
+    if peer == "nccl" or torch_dist.get_world_size(group) < 2:
+        return
+    if not torch.cuda.is_available():
+        if peer == "peer":
+            raise RuntimeError("vqb200.dist.enable(peer='peer'): no CUDA device")
+        _PEER_STATUS = "nccl (no CUDA device)"
+        return
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    try:
+        _PEER = PeerExchange(group, dev, slot_bytes)
+        _PEER_STATUS = "peer"
+    except RuntimeError as e:          # the same verdict on every rank (collective checks inside)
+        _PEER = None
+        if peer == "peer":
+            raise
+        _PEER_STATUS = f"nccl (peer memory unavailable: {e})"
+
+
+def _close_peer() -> None:
+    global _PEER
+    if _PEER is not None:
+        _PEER.close()
+        _PEER = None
 
 
 def disable() -> None:
-    global _GROUP, _ENABLED
-    _GROUP, _ENABLED = None, False
+    global _GROUP, _ENABLED, _PEER_STATUS
+    _close_peer()
+    _GROUP, _ENABLED, _PEER_STATUS = None, False, "off"
+
+
+def peer_exchange() -> Optional[PeerExchange]:
+    """The active peer-memory exchange, or None when the NCCL transport is in use."""
+    return _PEER if enabled() else None
+
+
+def peer_status() -> str:
+    return _PEER_STATUS
 
 
 def enabled() -> bool:

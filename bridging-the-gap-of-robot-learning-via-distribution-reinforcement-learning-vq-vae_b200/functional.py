@@ -217,7 +217,19 @@ class _RVQFn(torch.autograd.Function):
                                                         Wp.shape[0], ptr(r), ptr(W), ptr(st.ee), ptr(st.image),
                                                         ptr(st.info), K, ptr(idx[s]), ptr(ws), c_size_t(ws.numel()),
                                                         cfg.algo, stream), "vq_assign_residual")
-                if ema_train:
+                px = _dist.peer_exchange() if ema_train else None
+                if ema_train and px is not None and px.device == dev and px.fits(K, D):
+                    # K3a into this rank's slot of the symmetric buffer; K3b barriers and sums every rank's slot over
+                    # NVLink itself (csrc/peer.cu): no collective launch between the two
+                    epoch, my_slot, slots = px.next_slot()
+                    check(lib.vqb200_ema_accumulate(ptr(r), B, C, T, sB, sC, sT, ptr(idx[s]), None, K,
+                                                    ctypes.c_void_p(my_slot), 0, stream), "ema_accumulate")
+                    check(lib.vqb200_ema_finalize_peer(slots, px.flags, px.rank, px.world, ctypes.c_uint32(epoch),
+                                                       ptr(st.cnt), ptr(cfg.ema_cluster_size[s]), ptr(cfg.ema_w[s]),
+                                                       ptr(W), K, D, c_double(cfg.decay), c_double(cfg.eps), ptr(st.ee),
+                                                       ptr(st.image), ptr(st.info), ptr(st.scratch), stream),
+                          "ema_finalize_peer")
+                elif ema_train:
                     check(lib.vqb200_ema_accumulate(ptr(r), B, C, T, sB, sC, sT, ptr(idx[s]), None, K,
                                                     ptr(st.stats), 0, stream), "ema_accumulate")
                     _dist.all_reduce_stats(st.stats)
@@ -225,6 +237,7 @@ class _RVQFn(torch.autograd.Function):
                                                   ptr(W), K, D, c_double(cfg.decay), c_double(cfg.eps), ptr(st.ee),
                                                   ptr(st.image), ptr(st.info), ptr(st.scratch), stream),
                           "ema_finalize")
+                if ema_train:
                     st.mark_fresh(W)
                     if s == 0 and ctx.needs_input_grad[0]:
                         e0_snapshot = W.clone()       # a later call may update E_0 before backward runs

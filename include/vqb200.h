@@ -94,6 +94,38 @@ int vqb200_ema_finalize(const float* stats, float* ema_cluster_size, float* ema_
                         float* ee, void* image, float* info, float* scratch,
                         vqb200_stream_t stream);
 
+/* ---- K3b fused with its all-reduce over NVLink peer memory --------- SURVEY.md §8e ---------
+ * Data-parallel ranks of ONE node (one process per GPU) replace
+ *     ema_accumulate -> ncclAllReduce(stats) -> ema_finalize
+ * by accumulating straight into a slot of a symmetric buffer every rank has mapped, then calling
+ * vqb200_ema_finalize_peer: a one-shot flag barrier over peer memory, direct NVLink reads of every
+ * rank's [dw | cnt] slot summed in RANK ORDER (bit-identical result on all ranks, no broadcast),
+ * and the same decay / Laplace / normalise arithmetic as vqb200_ema_finalize (models/vqvae.py:46-50).
+ *
+ * vqb200_peer_alloc / _open / _close / _free are the only calls of this library that own device
+ * memory: the buffer must come from cudaMalloc (not a framework's sub-allocator) to be exportable
+ * with CUDA IPC.  `handle` is a 64-byte cudaIpcMemHandle_t the caller ships to its peers
+ * (torch.distributed.all_gather_object in the glue).  Suggested layout (what the glue uses):
+ *     [ flags: VQB200_MAX_PEERS x uint32, padded to 256 B | slot 0 | slot 1 ]
+ * peer_stats[p] / peer_flags[p] (HOST arrays of `world` device pointers): rank p's slot of the
+ * current epoch / rank p's flag words, as mapped into THIS process (own buffer for p == rank).
+ * `epoch` increases by one per call on every rank (slot = epoch & 1); flags start at 0, so the
+ * first epoch is 1.  cnt_out (K floats, may be NULL) receives the reduced counts for
+ * vqb200_vq_metrics.  A peer that does not arrive within 30 s traps the kernel (loud, no hang). */
+#define VQB200_MAX_PEERS 16
+#define VQB200_PEER_HANDLE_BYTES 64
+int vqb200_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle);
+int vqb200_peer_open(const unsigned char* handle, void** dev_ptr);
+int vqb200_peer_close(void* dev_ptr);
+int vqb200_peer_free(void* dev_ptr);
+int vqb200_peer_barrier(uint32_t* const* peer_flags, int32_t rank, int32_t world, uint32_t epoch,
+                        vqb200_stream_t stream);
+int vqb200_ema_finalize_peer(const float* const* peer_stats, uint32_t* const* peer_flags,
+                             int32_t rank, int32_t world, uint32_t epoch, float* cnt_out,
+                             float* ema_cluster_size, float* ema_w, float* E, int64_t K, int64_t D,
+                             double decay, double eps, float* ee, void* image, float* info,
+                             float* scratch, vqb200_stream_t stream);
+
 /* ---- code histogram only (eval / non-EMA) --------------- models/vqvae.py:66,71 (row a9) --- */
 int vqb200_vq_histogram(const int32_t* idx, int64_t N, int64_t K, float* cnt, vqb200_stream_t stream);
 
