@@ -201,6 +201,18 @@ int vqb200_peer_barrier(uint32_t* const* peer_flags, int32_t rank, int32_t world
   peer::Table t;
   const int rc = peer::fill_table(t, nullptr, peer_flags, rank, world, epoch, false);
   if (rc != VQB200_OK) return rc;
+  {
+    // CUDA loads kernels lazily, and loading may need a context-wide synchronisation: a first launch of the finalize
+    // kernels queued behind a barrier that is still spinning would stall the host.  Load them here, once.
+    static thread_local bool loaded = false;
+    if (!loaded) {
+      cudaFuncAttributes fa;
+      VQ_CUDA(cudaFuncGetAttributes(&fa, peer::finalize_cs_kernel));
+      VQ_CUDA(cudaFuncGetAttributes(&fa, peer::finalize_w_kernel));
+      VQ_CUDA(cudaFuncGetAttributes(&fa, peer::barrier_kernel));
+      loaded = true;
+    }
+  }
   peer::barrier_kernel<<<1, 32, 0, stream>>>(t);
   VQ_LAUNCH_CHECK("peer::barrier_kernel");
   return VQB200_OK;

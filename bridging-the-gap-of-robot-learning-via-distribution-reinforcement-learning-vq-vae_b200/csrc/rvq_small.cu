@@ -47,9 +47,11 @@ struct Args {
   float* m3;                                    // [S][3] loss, perplexity, dcr
 };
 
+// [dw (K*D) | cnt (K)] of one stage, padded so that every stage's dw stays 16-byte aligned (vector reductions)
+__host__ __device__ __forceinline__ long long stage_stats_floats(long long K) { return (K * (D + 1) + 3) & ~3LL; }
 __device__ __forceinline__ long long stats_offset(const Args& a, int s) {
   long long o = 0;
-  for (int i = 0; i < s; ++i) o += (long long)a.K[i] * (D + 1);
+  for (int i = 0; i < s; ++i) o += stage_stats_floats(a.K[i]);
   return o;
 }
 __device__ __forceinline__ long long scratch_offset(const Args& a, int s) {
@@ -687,7 +689,7 @@ int vqb200_rvq_small_eligible(int64_t N, int64_t D, int32_t S, const int64_t* K)
 
 size_t vqb200_rvq_small_workspace_floats(int32_t S, const int64_t* K) {
   size_t n = 0;
-  for (int s = 0; s < S; ++s) n += (size_t)K[s] * (small::D + 1) + (size_t)K[s] + 8;
+  for (int s = 0; s < S; ++s) n += (size_t)small::stage_stats_floats(K[s]) + (size_t)K[s] + 8;
   return n + 16;
 }
 
@@ -716,7 +718,7 @@ int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, in
     VQ_CHECK_ARG(!train_ema || (a.cs[s] && a.w[s]), VQB200_EINVAL, "rvq_small_forward: EMA buffers of stage %d missing", s);
     a.K[s] = (int)K[s];
     a.k_eps[s] = (float)((double)K[s] * eps);
-    stats_floats += (size_t)K[s] * (D + 1);
+    stats_floats += (size_t)stage_stats_floats(K[s]);
   }
   for (int s = S; s < MAX_S; ++s) { a.E[s] = nullptr; a.cs[s] = nullptr; a.w[s] = nullptr; a.K[s] = 0; a.k_eps[s] = 0.f; }
   VQ_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, VQB200_EALIGN, "rvq_small_forward: workspace must be 16-byte aligned");

@@ -62,6 +62,9 @@ def test_peer_finalize_in_process_ranks(K, D, world):
                       "cnt": torch.empty(K, device=dev), "st": _state(lib, K, D, dev), "stream": torch.cuda.Stream(dev)})
     slot_tab = (ctypes.c_void_p * world)(*[s.data_ptr() for s in slots])
     flag_tab = (ctypes.c_void_p * world)(*[f.data_ptr() for f in flags])
+    # two spinning kernels of one process must not wait on a lazily loaded third one: load everything first
+    warm = torch.zeros(64, dtype=torch.int32, device=dev)
+    check(lib.vqb200_peer_barrier((ctypes.c_void_p * 1)(warm.data_ptr()), 0, 1, ctypes.c_uint32(1), None), "peer_barrier")
     torch.cuda.synchronize()
     for epoch in (1, 2):                                   # second epoch: flags are reused, state has moved on
         for r, R in enumerate(ranks):
