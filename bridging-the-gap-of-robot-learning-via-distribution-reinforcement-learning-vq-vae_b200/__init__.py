@@ -13,8 +13,9 @@ from .quantizers import (  # noqa: F401
 )
 from . import dist  # noqa: F401
 from . import tokens  # noqa: F401
+from . import trainer  # noqa: F401
 from .graphs import GraphedQuantizerStep  # noqa: F401
 
 __all__ = ["VectorQuantizer", "ResidualVQ", "FSQ", "LFQ", "HybridVQ", "IdentityVQ",
            "vq_assign", "vq_quantize", "rvq_quantize", "fsq_round", "lfq_sign", "codebook_prepare",
-           "QuantizerState", "dist", "tokens", "GraphedQuantizerStep"]
+           "QuantizerState", "dist", "tokens", "trainer", "GraphedQuantizerStep"]

@@ -260,3 +260,32 @@ def test_revive_dead_codes_is_opt_in_and_deterministic(use_ema, contig):
     # (two dead codes may hash to the same row -> duplicate codes -> exact ties: compare distances, not indices)
     got = d.gather(1, mod.last_indices.reshape(-1, 1).long()).squeeze(1)
     assert float((got - d.min(1).values).abs().max()) < 1e-4
+
+
+def test_ddp_trainer_single_rank_writes_reference_format_checkpoints(tmp_path):
+    """<pkg>/trainer.py on one GPU: CLI of scripts/train_ablation.py, the reference's three
+    checkpoint files and log, loadable strictly by a fresh DualMotionVQVAE (what export_motion.py does)."""
+    import json
+    from vqb200 import trainer
+    from models.vqvae import DualMotionVQVAE
+    argv = ["--mode", "teacher", "--arch", "resnet_no_down", "--method", "ema", "--window", "10", "--epochs", "3",
+            "--batch_size", "256", "--synthetic", "700", "--data_root", str(tmp_path / "nodata"),
+            "--ckpt_dir", str(tmp_path / "ck"), "--log_dir", str(tmp_path / "res"), "--name", "t"]
+    args = trainer.build_parser().parse_args(argv)
+    hist = trainer.train_one_seed(args, 42, torch.device(DEV))
+    assert len(hist["train_loss"]) == 3 and all(v == v for v in hist["train_loss"])
+    run = "t_ema_teacher_seed_42"
+    last = torch.load(tmp_path / "ck" / f"{run}_last.pth", map_location=DEV)
+    assert set(last) == {"epoch", "model_state_dict", "optimizer_state_dict", "best_loss", "config"} and last["epoch"] == 2
+    assert (tmp_path / "ck" / f"{run}_best.pth").exists()
+    final = torch.load(tmp_path / "ck" / f"{run}_final.pth", map_location=DEV)
+    m = DualMotionVQVAE(human_input_dim=126, robot_input_dim=29, hidden_dim=64, arch="resnet_no_down", method="ema",
+                        window_size=10).to(DEV)
+    m.load_state_dict(final, strict=True)
+    # 630 training windows x 10 frames went through the EMA update every epoch: the cluster sizes moved off zero
+    assert float(m.quantizer.ema_cluster_size.sum()) > 0
+    assert json.load(open(tmp_path / "res" / "log_t_seed_42.json"))["train_loss"] == hist["train_loss"]
+    # resume picks up at epoch 3 and trains nothing more
+    args2 = trainer.build_parser().parse_args(argv + ["--resume"])
+    hist2 = trainer.train_one_seed(args2, 42, torch.device(DEV))
+    assert hist2["train_loss"] == hist["train_loss"]
