@@ -88,7 +88,7 @@ def load(build_if_missing=True):
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
+    path = os.environ.get("VQB200_LIB_PATH") or _build.LIB      # development: A/B builds of the same sources
     if build_if_missing and (not os.path.exists(path) or (os.environ.get("VQB200_REBUILD") == "1")):
         _build.build()
     if not os.path.exists(path):

@@ -37,6 +37,7 @@ def build(force=False, verbose=False):
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("VQB200_NVCC_EXTRA", "").split()          # development: e.g. -DVQB200_TOP2_VARIANT=0
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     procs = []
     for s in srcs:

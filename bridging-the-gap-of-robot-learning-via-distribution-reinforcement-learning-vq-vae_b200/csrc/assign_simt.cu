@@ -188,10 +188,11 @@ int launch_assign_simt(const ZView& z, const float* E, const float* ee, int K, i
   using namespace simt;
   const size_t smem = assign_simt_smem_bytes(D);
   VQ_CHECK_ARG(smem <= 227 * 1024, VQB200_ESHAPE, "vq_assign(SIMT): D=%d needs %zu B of shared memory (max 232448)", D, smem);
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static PerDevice configured_;
+  std::atomic<size_t>& configured = configured_.here();
+  if (smem > 48 * 1024 && smem > configured.load()) {
     VQ_CUDA(cudaFuncSetAttribute(vq_assign_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    configured.store(smem);
   }
   const int Dp = (D + BK - 1) / BK * BK;
   const long long tiles = (max_rows + BM - 1) / BM;

@@ -415,10 +415,11 @@ int launch_assign_tc(const ZView& z, const float* E, const float* ee, const void
   VQ_CHECK_ARG(workspace_bytes >= assign_tc_workspace_bytes(z.N), VQB200_EWORKSPACE, "vq_assign(TC): workspace too small");
   VQ_CHECK_ARG((reinterpret_cast<uintptr_t>(image) & 1023) == 0, VQB200_EALIGN, "vq_assign(TC): image must be 1024-byte aligned");
   VQ_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, VQB200_EALIGN, "vq_assign(TC): workspace must be 16-byte aligned");
-  static thread_local bool configured = false;
-  if (!configured) {
+  static PerDevice configured_;
+  std::atomic<size_t>& configured = configured_.here();
+  if (!configured.load()) {
     VQ_CUDA(cudaFuncSetAttribute(vq_assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    configured = true;
+    configured.store(1);
   }
   int32_t* wsi = reinterpret_cast<int32_t*>(workspace);
   VQ_CUDA(cudaMemsetAsync(wsi, 0, 256, stream));

@@ -264,10 +264,11 @@ static int launch_kb(const Params& p, cudaStream_t stream) {
   constexpr int smem = (STREAM_A ? 0 : KB * A_BLOCK) + NST * (IMG_TILE_BYTES + (STREAM_A ? A_BLOCK : 0)) + SMEM_NH + SMEM_BAR +
                        (EPI8 ? SMEM_XCH : 0);
   static_assert(smem <= 232448, "shared memory budget");
-  static thread_local bool configured = false;
-  if (!configured) {
+  static PerDevice configured_;
+  std::atomic<size_t>& configured = configured_.here();
+  if (!configured.load()) {
     VQ_CUDA(cudaFuncSetAttribute(vq_assign_tc_gen_kernel<KB, NST, EPI8, STREAM_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured.store(1);
   }
   const int grid = (int)max(1LL, min(p.ntiles, (long long)sm_count()));
   vq_assign_tc_gen_kernel<KB, NST, EPI8, STREAM_A><<<grid, NTHREADS, smem, stream>>>(p);
@@ -319,10 +320,11 @@ int launch_assign_tc_gen(const ZView& z, const float* E, const float* ee, const 
   {
     const int sub_rows = (D <= 256) ? TILE_M : TILE_M / 2;          // D = 512: two 64-row passes per image tile
     const size_t smem = (size_t)sub_rows * (D + 4) * sizeof(float);
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static PerDevice configured_;
+    std::atomic<size_t>& configured = configured_.here();
+    if (smem > 48 * 1024 && smem > configured.load()) {
       VQ_CUDA(cudaFuncSetAttribute(z_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
+      configured.store(smem);
     }
     const long long work = p.ntiles * (TILE_M / sub_rows);
     const int grid = (int)max(1LL, min(work, (long long)sm_count() * (smem > 100 * 1024 ? 1 : 2)));

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
+#include <atomic>
 
 #include "../../include/vqb200.h"
 
@@ -17,6 +18,14 @@ int  fail(int code, const char* fmt, ...);
 int  cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
 int  sm_count();
+int  current_device();           // cudaGetDevice() & 63
+
+// cudaFuncSetAttribute / occupancy answers are per DEVICE: a call site remembers what it has configured per device
+// (a static zero-initialised instance per site; racing first calls configure twice, which is harmless).
+struct PerDevice {
+  std::atomic<size_t> v[64];
+  std::atomic<size_t>& here() { return v[current_device()]; }
+};
 
 #define VQ_CHECK_ARG(cond, code, ...) do { if (!(cond)) return ::vqb200::fail((code), __VA_ARGS__); } while (0)
 #define VQ_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return ::vqb200::cuda_fail(e__, #expr); } while (0)

@@ -283,10 +283,11 @@ int vqb200_ema_accumulate(const float* z, int64_t B, int64_t C, int64_t T, int64
   const int use_hist = (K <= ACC_HIST_MAX) ? 1 : 0;
   const size_t smem = (size_t)ACC_BM * (D + 4) * sizeof(float) + (use_hist ? (size_t)K * sizeof(int) : 0);
   VQ_CHECK_ARG(smem <= 227 * 1024, VQB200_ESHAPE, "ema_accumulate: D=%d K=%lld needs %zu B of shared memory", D, (long long)K, smem);
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static PerDevice configured_;
+  std::atomic<size_t>& configured = configured_.here();
+  if (smem > 48 * 1024 && smem > configured.load()) {
     VQ_CUDA(cudaFuncSetAttribute(ema_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    configured.store(smem);
   }
   const long long tiles = (zv.N + ACC_BM - 1) / ACC_BM;
   const int per_sm = smem > 100 * 1024 ? 1 : (smem > 56 * 1024 ? 2 : 4);

@@ -433,11 +433,16 @@ static int launch_fused(const FusedParams& p, cudaStream_t stream) {
 #define VQ_FUSED_CASE(DQ)                                                                                             \
   do {                                                                                                                \
     auto kern = BWD ? fused_backward_kernel<IS_LFQ, DQ> : fused_forward_kernel<IS_LFQ, DQ>;                           \
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fsq_lfq_fused)");                                 \
-    int per_sm_now = 0;                                                                                               \
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_now, kern, F_NT, smem);                                 \
-    if (e != cudaSuccess || per_sm_now < 1) return cuda_fail(e, "occupancy(fsq_lfq_fused)");                          \
+    static PerDevice occ_;                       /* resident CTAs per SM of this instantiation, per device (0 = unknown) */ \
+    std::atomic<size_t>& occ = occ_.here();                                                                           \
+    int per_sm_now = (int)occ.load();                                                                                 \
+    if (per_sm_now == 0) {                                                                                            \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fsq_lfq_fused)");                               \
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_now, kern, F_NT, smem);                               \
+      if (e != cudaSuccess || per_sm_now < 1) return cuda_fail(e, "occupancy(fsq_lfq_fused)");                        \
+      occ.store((size_t)per_sm_now);                                                                                  \
+    }                                                                                                                 \
     const int grid_now = (int)max(1LL, min(p.ntiles, (long long)sm_count() * per_sm_now));                            \
     kern<<<grid_now, F_NT, smem, stream>>>(p);                                                                            \
   } while (0)

@@ -204,13 +204,14 @@ int vqb200_peer_barrier(uint32_t* const* peer_flags, int32_t rank, int32_t world
   {
     // CUDA loads kernels lazily, and loading may need a context-wide synchronisation: a first launch of the finalize
     // kernels queued behind a barrier that is still spinning would stall the host.  Load them here, once.
-    static thread_local bool loaded = false;
-    if (!loaded) {
+    static PerDevice loaded_;
+    std::atomic<size_t>& loaded = loaded_.here();
+    if (!loaded.load()) {
       cudaFuncAttributes fa;
       VQ_CUDA(cudaFuncGetAttributes(&fa, peer::finalize_cs_kernel));
       VQ_CUDA(cudaFuncGetAttributes(&fa, peer::finalize_w_kernel));
       VQ_CUDA(cudaFuncGetAttributes(&fa, peer::barrier_kernel));
-      loaded = true;
+      loaded.store(1);
     }
   }
   peer::barrier_kernel<<<1, 32, 0, stream>>>(t);

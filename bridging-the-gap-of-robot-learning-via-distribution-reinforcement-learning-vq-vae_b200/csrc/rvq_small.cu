@@ -731,13 +731,20 @@ int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, in
     long long slice_codes = 0;
     for (int s = 0; s < S; ++s) slice_codes += (K[s] + wide::CS - 1) / wide::CS;
     static const int wide_off = [] { const char* e = getenv("VQB200_RVQ_SMALL_NARROW"); return e ? atoi(e) : 0; }();
-    static thread_local int coop = -1;
-    if (coop < 0) {
+    // per device: 0 = not probed, 1 = no cooperative launch, 2 + n = n co-resident 8-CTA clusters (GPC floor-planning
+    // decides, not SMs / 8)
+    static PerDevice probe_;
+    std::atomic<size_t>& probe = probe_.here();
+    int coop = 0, max_rb = 0;
+    if (probe.load() == 0) {
       int dev = 0, v = 0;
       coop = (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && v) ? 1 : 0;
+      if (!coop) probe.store(1);
+    } else {
+      coop = probe.load() >= 2 ? 1 : 0;
+      max_rb = coop ? (int)probe.load() - 2 : 0;
     }
-    static thread_local int max_rb = -1;             // co-resident 8-CTA clusters (GPC floor-planning decides, not SMs / 8)
-    if (coop == 1 && max_rb < 0) {
+    if (coop == 1 && probe.load() == 0) {
       VQ_CUDA(cudaFuncSetAttribute(wide::rvq_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide::SMEM_BYTES));
       cudaLaunchConfig_t q = {};
       q.gridDim = dim3(wide::MAX_RB * wide::CS); q.blockDim = dim3(wide::NT); q.dynamicSmemBytes = wide::SMEM_BYTES;
@@ -747,7 +754,8 @@ int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, in
       q.attrs = qa; q.numAttrs = 1;
       int nc = 0;
       if (cudaOccupancyMaxActiveClusters(&nc, wide::rvq_wide_kernel, &q) != cudaSuccess) { cudaGetLastError(); nc = 0; }
-      max_rb = nc > wide::MAX_RB ? wide::MAX_RB : nc;
+      max_rb = nc > wide::MAX_RB ? wide::MAX_RB : (nc < 0 ? 0 : nc);
+      probe.store(2 + (size_t)max_rb);
     }
     if (!wide_off && coop == 1 && max_rb >= 4 && B * T <= (long long)max_rb * wide::MAX_RPB &&
         slice_codes <= wide::MAX_SLICE_CODES) {
@@ -777,11 +785,12 @@ int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, in
 
   const size_t smem = ((size_t)MAX_ROWS_PER_CTA * LDR + MAX_K + 8 * 32 + (size_t)CHUNK * D) * sizeof(float) +
                       (8 * 32 + MAX_ROWS_PER_CTA) * sizeof(int);
-  static thread_local bool configured = false;
-  if (!configured) {
+  static PerDevice configured_;
+  std::atomic<size_t>& configured = configured_.here();
+  if (!configured.load()) {
     VQ_CUDA(cudaFuncSetAttribute(rvq_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VQ_CUDA(cudaFuncSetAttribute(rvq_small_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    configured = true;
+    configured.store(1);
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CLUSTER);

@@ -72,6 +72,19 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 
 // Running top-2 of one 32-column chunk of scores: s = acc + nh (nh = -|E|^2/2), column index packed into the low
 // 7 mantissa bits, 3.5 ALU ops per score.  `base` = first column of the chunk inside the 128-code tile.
+#ifndef VQB200_TOP2_VARIANT
+#define VQB200_TOP2_VARIANT 0      // measured on B200 (vq_assign, 10 M x 1024, one variant per build): V = 0 4.26 ms,
+                                   // V = 1 4.37 ms, V = 2 4.54 ms -- the epilogue warps are bound by their own instruction
+                                   // count (4.5 / 5.0 / 5.5 per score), not by the alu pipe, so V = 0 stays
+#endif
+constexpr int TOP2_VARIANT = VQB200_TOP2_VARIANT;
+// V selects where the runner-up arithmetic runs (an experiment kept for the record: moving min() from the alu pipe to
+// add/sub on the fma pipe is legal because t2 only feeds the inequality g1 - g2 > thr, whose budget covers a few ulps):
+//   V = 0: lo = min(p0,p1), m = min(t1,hi)                      3.5 alu + 1 fma ops per score
+//   V = 1: m = (t1 + hi) - max(t1,hi)  on the fma pipe          3.0 alu + 2 fma
+//   V = 2: additionally lo = (p0 + p1) - hi                     2.5 alu + 3 fma
+// (-inf) - (-inf) = NaN is harmless: max.f32 drops NaN operands, exactly what a -inf candidate would have done.
+template <int V = TOP2_VARIANT>
 __device__ __forceinline__ void top2_chunk(const uint32_t (&cur)[32], const float4* nh, int base, uint32_t mask,
                                            float& t1, float& t2) {
 #pragma unroll
@@ -82,12 +95,22 @@ __device__ __forceinline__ void top2_chunk(const uint32_t (&cur)[32], const floa
     const float p1 = pack_col(__uint_as_float(cur[e4 * 4 + 1]) + h.y, col + 1, mask);
     const float p2 = pack_col(__uint_as_float(cur[e4 * 4 + 2]) + h.z, col + 2, mask);
     const float p3 = pack_col(__uint_as_float(cur[e4 * 4 + 3]) + h.w, col + 3, mask);
-    const float hi0 = fmaxf(p0, p1), lo0 = fminf(p0, p1);
-    t2 = fmax3(t2, lo0, fminf(t1, hi0));
-    t1 = fmaxf(t1, hi0);
-    const float hi1 = fmaxf(p2, p3), lo1 = fminf(p2, p3);
-    t2 = fmax3(t2, lo1, fminf(t1, hi1));
-    t1 = fmaxf(t1, hi1);
+    {
+      const float hi = fmaxf(p0, p1);
+      const float lo = (V >= 2) ? __fsub_rn(__fadd_rn(p0, p1), hi) : fminf(p0, p1);
+      const float tn = fmaxf(t1, hi);
+      const float m = (V >= 1) ? __fsub_rn(__fadd_rn(t1, hi), tn) : fminf(t1, hi);
+      t2 = fmax3(t2, lo, m);
+      t1 = tn;
+    }
+    {
+      const float hi = fmaxf(p2, p3);
+      const float lo = (V >= 2) ? __fsub_rn(__fadd_rn(p2, p3), hi) : fminf(p2, p3);
+      const float tn = fmaxf(t1, hi);
+      const float m = (V >= 1) ? __fsub_rn(__fadd_rn(t1, hi), tn) : fminf(t1, hi);
+      t2 = fmax3(t2, lo, m);
+      t1 = tn;
+    }
   }
 }
 
@@ -96,7 +119,8 @@ __device__ __forceinline__ void top2_chunk(const uint32_t (&cur)[32], const floa
 // -|E|^2/2 add + 7 index bits packed into the mantissa.  mag = |x| * max|E|.
 __device__ __forceinline__ float score_error_bound(float mag, float emax, int D) {
   const float acc = 3.0f * (float)D * 1.2e-7f;
-  return (1.15e-5f + acc + 1.6e-5f) * mag + 1.7e-5f * (0.5f * emax * emax);
+  // + 1e-6 on both terms: the runner-up may be formed by add/sub on the fma pipe (top2_chunk<V > 0>)
+  return (1.15e-5f + acc + 1.6e-5f + 1.0e-6f) * mag + 1.8e-5f * (0.5f * emax * emax);
 }
 
 }  // namespace tcc

@@ -459,14 +459,15 @@ int try_gather_tile(const ZView& z, const float* E, const int32_t* idx, int K, i
   static const bool use_bulk = !(getenv("VQB200_NO_BULK") && atoi(getenv("VQB200_NO_BULK")));
   if (use_bulk && (g.rows_per_tile * g.D * 4) % 16 == 0) {
     const size_t smem = (size_t)2 * (two ? 2 : 1) * TILE_ELEMS * sizeof(float);
-    static thread_local bool configured = false;
-    if (!configured) {
+    static PerDevice configured_;
+    std::atomic<size_t>& configured = configured_.here();
+    if (!configured.load()) {
       cudaError_t e1 = cudaFuncSetAttribute(gather_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             2 * 2 * TILE_ELEMS * (int)sizeof(float));
       cudaError_t e2 = cudaFuncSetAttribute(gather_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             CHAIN_STAGES * TILE_ELEMS * (int)sizeof(float));
       if (e1 != cudaSuccess || e2 != cudaSuccess) return cuda_fail(e1 != cudaSuccess ? e1 : e2, "cudaFuncSetAttribute(gather_bulk_kernel)");
-      configured = true;
+      configured.store(1);
     }
     const int grid = tile_grid(g, two ? 3 : 6);
     if (two) gather_bulk_kernel<true><<<grid, TILE_NT, smem, stream>>>(z.p, E, idx, K, g, mode, o1, o2, in2, accum_init, g_loss, coef, sse);
@@ -531,11 +532,12 @@ int try_accumulate_tile(const ZView& z, const int32_t* idx, const float* E, int 
   if ((reinterpret_cast<uintptr_t>(dw) & 15) || (mode == 1 && (reinterpret_cast<uintptr_t>(E) & 15))) return 0;
   const int use_hist = K <= 8192 ? 1 : 0;
   const size_t smem = ACC_TILE_ELEMS * sizeof(float) + (use_hist ? (size_t)K * sizeof(int) : 0);
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
+  static PerDevice configured_;
+  std::atomic<size_t>& configured = configured_.here();
+  if (smem > configured.load()) {
     cudaError_t e = cudaFuncSetAttribute(accumulate_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(accumulate_tile_kernel)");
-    configured = smem;
+    configured.store(smem);
   }
   accumulate_tile_kernel<<<tile_grid(g, 4), TILE_NT, smem, stream>>>(z.p, idx, E, K, g, dw, cnt, mode, use_hist);
   count_launch();
