@@ -45,6 +45,7 @@ struct Args {
   int32_t* idx;                                 // [S][N]
   float* out;                                   // [B,C,T] contiguous
   float* m3;                                    // [S][3] loss, perplexity, dcr
+  int stamps;                                   // development (VQB200_RVQ_STAMPS): CTA 0 prints per-phase globaltimer stamps
 };
 
 // [dw (K*D) | cnt (K)] of one stage, padded so that every stage's dw stays 16-byte aligned (vector reductions)
@@ -354,11 +355,11 @@ rvq_small_kernel(const Args a) {
 namespace wide {
 using small::Args;
 using small::stats_offset;
-constexpr int D = 64, NT = 256, CS = 8, MAX_RB = 16;    // code slices (cluster size), row blocks (runtime: as many 8-CTA
+constexpr int D = 64, NT = 512, NW = NT / 32, CS = 8, MAX_RB = 16;    // code slices (cluster size), row blocks (runtime: as many 8-CTA
                                                         // clusters as the device can keep co-resident, at most 16)
 constexpr int MAX_RPB = 64;                             // rows per block  (N <= 1024)
 constexpr int MAX_SLICE_CODES = 384;                    // sum over stages of ceil(K_s / 8)  (S*K <= 3072)
-constexpr int LDR = D + 1;
+constexpr int LDR = D + 4, LDE = D + 4;                 // row pitches: 16-byte aligned, bank-conflict-free tiles
 constexpr unsigned SPIN_LIMIT = 1u << 24;
 
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& generation, unsigned nblocks) {
@@ -372,7 +373,11 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& genera
       unsigned v;
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
       if (v >= target) break;
-      if (++spins > SPIN_LIMIT) __trap();
+      if (++spins > SPIN_LIMIT) {
+        printf("vqb200 rvq_wide_kernel: grid barrier timed out in CTA %d (generation %u: %u of %u arrivals)\n",
+               (int)blockIdx.x, generation, v, target);
+        __trap();
+      }
     }
     __threadfence();
   }
@@ -380,23 +385,34 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& genera
   __syncthreads();
 }
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define VQ_STAMP(i) do { if (a.stamps && blockIdx.x == 0 && threadIdx.x == 0 && (i) < 64) { stamp[(i)] = gtime(); if ((i) == 0) cyc0 = clock64(); } } while (0)
+
 __global__ void __launch_bounds__(NT, 1)
 rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
+  __shared__ unsigned long long stamp[64];
+  long long cyc0 = 0;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) float smem[];
   float* R = smem;                                  // [MAX_RPB][LDR] running residual (private copy of the row block)
   float* O = R + MAX_RPB * LDR;                     // [MAX_RPB][LDR] running sum of the straight-through values
-  float* Es = O + MAX_RPB * LDR;                    // [MAX_SLICE_CODES][D] this CTA's code slice of every stage
-  float* ees = Es + MAX_SLICE_CODES * D;            // [MAX_SLICE_CODES] |E_k|^2
+  float* Es = O + MAX_RPB * LDR;                    // [MAX_SLICE_CODES][LDE] this CTA's code slice of every stage
+  float* ees = Es + MAX_SLICE_CODES * LDE;            // [MAX_SLICE_CODES] |E_k|^2
   float* csn = ees + MAX_SLICE_CODES;               // [MAX_K] cs' of the current stage
-  float* bestd = csn + small::MAX_K;                // [8 warps][32]
-  int* bestk = reinterpret_cast<int*>(bestd + 8 * 32);
-  int* rowk = bestk + 8 * 32;                       // [MAX_RPB]
+  float* xxs = csn + small::MAX_K;                  // [MAX_RPB] |x|^2 of the current residual rows
+  int* rowk = reinterpret_cast<int*>(xxs + MAX_RPB); // [MAX_RPB]
   unsigned long long* ckey = reinterpret_cast<unsigned long long*>(rowk + MAX_RPB);   // [MAX_RPB] this slice's candidates
-  __shared__ double red[8];
+  __shared__ double red[NW];
   __shared__ float s_n;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (a.stamps && tid < 64) stamp[tid] = 0;
+  __syncthreads();
+  VQ_STAMP(0);
   const int slice = (int)cluster.block_rank();      // code slice 0..7
   const int rb = blockIdx.x / CS;                   // row block 0..15
   const unsigned nblocks = gridDim.x;
@@ -409,29 +425,66 @@ rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
   const int rows = (int)max(0LL, min((long long)rpb, N - row0));
   const int C = (int)a.z.C, T = (int)a.z.T;
 
-  // ---- prologue: rows, and this CTA's slice of every stage's (pre-update) codebook with |E|^2 ----
-  for (int i = tid; i < rows * D; i += NT) {
-    const int r = i / D, k = i - r * D;
-    R[r * LDR + k] = __ldg(a.z.p + a.z.row_base(row0 + r) + (long long)k * a.z.sC);
-    O[r * LDR + k] = 0.f;
+  // ---- prologue: rows, and this CTA's slice of every stage's (pre-update) codebook with |E|^2.  All global loads of
+  //      a batch are issued before the first store: one L2 round trip per batch instead of one per element ----
+  for (int i0 = tid; i0 < rows * D; i0 += NT * 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * NT;
+      const int r = i / D, k = i - r * D;
+      v[u] = (i < rows * D) ? __ldg(a.z.p + a.z.row_base(row0 + r) + (long long)k * a.z.sC) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * NT;
+      if (i < rows * D) { const int r = i / D, k = i - r * D; R[r * LDR + k] = v[u]; O[r * LDR + k] = 0.f; }
+    }
   }
+  VQ_STAMP(50);
   int sl_off[small::MAX_S + 1];                     // slice offsets (codes) inside Es per stage
   sl_off[0] = 0;
 #pragma unroll
   for (int s = 0; s < small::MAX_S; ++s) sl_off[s + 1] = sl_off[s] + (s < a.S ? (a.K[s] + CS - 1) / CS : 0);
-  for (int s = 0; s < a.S; ++s) {
-    const int per = (a.K[s] + CS - 1) / CS;
-    const int k0 = min(a.K[s], slice * per), k1 = min(a.K[s], k0 + per);
-    const float4* src = reinterpret_cast<const float4*>(a.E[s] + (size_t)k0 * D);
-    float4* dst = reinterpret_cast<float4*>(Es + (size_t)sl_off[s] * D);
-    for (int i = tid; i < (k1 - k0) * (D / 4); i += NT) dst[i] = __ldg(src + i);
+  {
+    // the slices of all stages as ONE flattened list of float4 (the destination is contiguous in Es by construction;
+    // a short slice -- K not a multiple of 8 -- leaves its tail of the reserved range untouched and unread)
+    const int total4 = sl_off[a.S] * (D / 4);
+    float4* dst = reinterpret_cast<float4*>(Es);
+    for (int i0 = tid; i0 < total4; i0 += NT * 8) {
+      float4 v[8]; bool ok[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * NT;
+        ok[u] = false;
+        if (i < total4) {
+          const int code = i / (D / 4);
+          int st = 0;
+#pragma unroll
+          for (int q = 1; q < small::MAX_S; ++q) st += (q < a.S && code >= sl_off[q]) ? 1 : 0;
+          const int per = (a.K[st] + CS - 1) / CS;
+          const int k0 = min(a.K[st], slice * per), k1 = min(a.K[st], k0 + per);
+          const int kl = code - sl_off[st];
+          if (kl < k1 - k0) {
+            ok[u] = true;
+            v[u] = __ldg(reinterpret_cast<const float4*>(a.E[st] + (size_t)(k0 + kl) * D) + (i - code * (D / 4)));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * NT;
+        if (ok[u]) dst[(i / (D / 4)) * (LDE / 4) + (i & (D / 4 - 1))] = v[u];
+      }
+    }
   }
   __syncthreads();
+  VQ_STAMP(51);
   for (int s = 0; s < a.S; ++s) {
     const int per = (a.K[s] + CS - 1) / CS;
     const int k0 = min(a.K[s], slice * per), k1 = min(a.K[s], k0 + per);
     for (int k = tid; k < k1 - k0; k += NT) {
-      const float4* e4 = reinterpret_cast<const float4*>(Es + (size_t)(sl_off[s] + k) * D);
+      const float4* e4 = reinterpret_cast<const float4*>(Es + (size_t)(sl_off[s] + k) * LDE);
       float acc = 0.f;
 #pragma unroll
       for (int c = 0; c < D / 4; ++c) {             // same summation order as the narrow kernel / codebook_prepare
@@ -443,92 +496,96 @@ rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
   }
   __syncthreads();
 
-  // in-place EMA update of one stage, this CTA's share of the codes (all 128 CTAs split the codebook)
-  auto update_stage = [&](int sp, float n) {
-    const int Kp = a.K[sp];
-    const float* dwp = a.stats + stats_offset(a, sp);
-    const float* cntp = dwp + (long long)Kp * D;
-    float* csp = a.cs[sp]; float* wv = a.w[sp]; float* Ep = a.E[sp];
-    const int per = (Kp + (int)nblocks - 1) / (int)nblocks;
-    const int k0 = min(Kp, cta * per), k1 = min(Kp, k0 + per);
-    for (int i = tid; i < (k1 - k0) * (D / 4); i += NT) {
-      const int k = k0 + i / (D / 4);
-      const float csv = fmaf(__ldcg(cntp + k), a.one_minus_decay, __fmul_rn(__ldcg(csp + k), a.decay));
-      const float cl = __fmul_rn(__fdiv_rn(__fadd_rn(csv, a.eps), __fadd_rn(n, a.k_eps[sp])), n);
-      const size_t q = (size_t)k0 * (D / 4) + i;
-      const float4 d0 = __ldcg(reinterpret_cast<const float4*>(dwp) + q);
-      const float4 w0 = __ldcg(reinterpret_cast<const float4*>(wv) + q);
-      float4 n0;
-      n0.x = fmaf(d0.x, a.one_minus_decay, __fmul_rn(w0.x, a.decay)); n0.y = fmaf(d0.y, a.one_minus_decay, __fmul_rn(w0.y, a.decay));
-      n0.z = fmaf(d0.z, a.one_minus_decay, __fmul_rn(w0.z, a.decay)); n0.w = fmaf(d0.w, a.one_minus_decay, __fmul_rn(w0.w, a.decay));
-      reinterpret_cast<float4*>(wv)[q] = n0;
-      reinterpret_cast<float4*>(Ep)[q] = make_float4(__fdiv_rn(n0.x, cl), __fdiv_rn(n0.y, cl), __fdiv_rn(n0.z, cl), __fdiv_rn(n0.w, cl));
-    }
-    __syncthreads();                                  // every thread has read the old cs of the slice
-    for (int k = k0 + tid; k < k1; k += NT)
-      csp[k] = fmaf(__ldcg(cntp + k), a.one_minus_decay, __fmul_rn(__ldcg(csp + k), a.decay));
-  };
-  float n_prev = 0.f;
+  float n_of[small::MAX_S];                         // n = sum(cs') of every stage (for the deferred in-place updates)
+#pragma unroll
+  for (int i = 0; i < small::MAX_S; ++i) n_of[i] = 0.f;
+  VQ_STAMP(53);
 
   for (int s = 0; s < a.S; ++s) {
+    VQ_STAMP(1 + s * 8 + 0);
     const int K = a.K[s];
     float* dw = a.stats + stats_offset(a, s);
     float* cnt = dw + (long long)K * D;
     const int per = (K + CS - 1) / CS;
     const int k0s = min(K, slice * per), ks = min(K, k0s + per) - k0s;      // this CTA's codes [k0s, k0s + ks)
-    const float* Esl = Es + (size_t)sl_off[s] * D;
+    const float* Esl = Es + (size_t)sl_off[s] * LDE;
     const float* eesl = ees + sl_off[s];
 
-    // ---- K1: exact fp32 distances + argmin over this CTA's code slice (lane = row, 64 registers) ----
+    // ---- K1: exact fp32 distances + argmin over this CTA's code slice.  Register-tiled: a warp owns a tile of 32 rows
+    //      x 16 codes, a lane 4 rows x 4 codes (rows i*8 + rg, codes j*4 + cg: with the padded row pitches every 16-byte
+    //      shared load of a warp touches 32 distinct banks), so one step of 4 dims costs 8 one-wavefront loads for 64
+    //      FMAs per lane.  (The earlier lane = row scheme broadcast one code vector per 4 FMAs and was bound by shared
+    //      memory bandwidth: 4.7 us per stage.)  Every (row, code) dot product is still ONE sequential fmaf chain over
+    //      dims 0..63, so distances -- and ties -- are bit-identical to the other exact paths ----
     {
-      const int nb = (rows + 31) >> 5;                // 1 or 2 sub-blocks of 32 rows
-      const int G = nb <= 1 ? 8 : 4;                  // warps per sub-block
-      const int blk = warp / G, sub = warp % G;
-      const int r = blk * 32 + lane;
-      const bool valid = blk < nb && r < rows;
-      float x[D];
-      float xx = 0.f;
+      for (int r = tid; r < rows; r += NT) {          // |x|^2 per row, the same fmaf chain as everywhere else
+        const float* xr = R + r * LDR;
+        float xx = 0.f;
 #pragma unroll
-      for (int c = 0; c < D; ++c) { x[c] = valid ? R[r * LDR + c] : 0.f; xx = fmaf(x[c], x[c], xx); }
-      float bd = INFINITY; int bk = INT_MAX;
-      if (blk < nb) {
-        for (int kk = sub; kk < ks; kk += 4 * G) {
-          const float4* e0 = reinterpret_cast<const float4*>(Esl + kk * D);       // warp-uniform: broadcast
-          const float4* e1 = reinterpret_cast<const float4*>(Esl + min(kk + G, ks - 1) * D);
-          const float4* e2 = reinterpret_cast<const float4*>(Esl + min(kk + 2 * G, ks - 1) * D);
-          const float4* e3 = reinterpret_cast<const float4*>(Esl + min(kk + 3 * G, ks - 1) * D);
-          float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+        for (int c = 0; c < D; ++c) xx = fmaf(xr[c], xr[c], xx);
+        xxs[r] = xx;
+        ckey[r] = cand_key(INFINITY, INT_MAX);
+      }
+      __syncthreads();
+      if (s == 0) VQ_STAMP(40);
+      const int rg = lane >> 2, cg = lane & 3;
+      const int code_blocks = (ks + 15) >> 4;
+      const int tiles = ((rows + 31) >> 5) * code_blocks;
+      for (int t = warp; t < tiles; t += NW) {
+        const int rblk = t / code_blocks, cblk = t - rblk * code_blocks;
+        int rI[4], kI[4];
 #pragma unroll
-          for (int c = 0; c < D / 4; ++c) {
-            const float4 v0 = e0[c], v1 = e1[c], v2 = e2[c], v3 = e3[c];
-            d0 = fmaf(x[4 * c], v0.x, d0); d1 = fmaf(x[4 * c], v1.x, d1); d2 = fmaf(x[4 * c], v2.x, d2); d3 = fmaf(x[4 * c], v3.x, d3);
-            d0 = fmaf(x[4 * c + 1], v0.y, d0); d1 = fmaf(x[4 * c + 1], v1.y, d1); d2 = fmaf(x[4 * c + 1], v2.y, d2); d3 = fmaf(x[4 * c + 1], v3.y, d3);
-            d0 = fmaf(x[4 * c + 2], v0.z, d0); d1 = fmaf(x[4 * c + 2], v1.z, d1); d2 = fmaf(x[4 * c + 2], v2.z, d2); d3 = fmaf(x[4 * c + 2], v3.z, d3);
-            d0 = fmaf(x[4 * c + 3], v0.w, d0); d1 = fmaf(x[4 * c + 3], v1.w, d1); d2 = fmaf(x[4 * c + 3], v2.w, d2); d3 = fmaf(x[4 * c + 3], v3.w, d3);
-          }
-          const float dots[4] = {d0, d1, d2, d3};
+        for (int i = 0; i < 4; ++i) { rI[i] = rblk * 32 + i * 8 + rg; kI[i] = cblk * 16 + i * 4 + cg; }
+        const float4* xp[4]; const float4* ep[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int kl = kk + u * G;
-            if (kl < ks) {
-              const int k = k0s + kl;
-              const float dd = __fsub_rn(__fadd_rn(xx, eesl[kl]), __fmul_rn(2.0f, dots[u]));
-              if (cand_better(dd, k, bd, bk)) { bd = dd; bk = k; }
+        for (int i = 0; i < 4; ++i) {
+          xp[i] = reinterpret_cast<const float4*>(R + min(rI[i], rows - 1) * LDR);
+          ep[i] = reinterpret_cast<const float4*>(Esl + min(kI[i], ks - 1) * LDE);
+        }
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+        for (int c = 0; c < D / 4; ++c) {
+          float4 xv[4], ev[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { xv[i] = xp[i][c]; ev[i] = ep[i][c]; }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float d = acc[i][j];
+              d = fmaf(xv[i].x, ev[j].x, d); d = fmaf(xv[i].y, ev[j].y, d);
+              d = fmaf(xv[i].z, ev[j].z, d); d = fmaf(xv[i].w, ev[j].w, d);
+              acc[i][j] = d;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          unsigned long long best = ~0ull;
+          const float xx = xxs[min(rI[i], rows - 1)];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (kI[j] < ks) {
+              const float dd = __fsub_rn(__fadd_rn(xx, eesl[kI[j]]), __fmul_rn(2.0f, acc[i][j]));
+              const unsigned long long key = cand_key(dd, k0s + kI[j]);
+              best = key < best ? key : best;
             }
           }
+          unsigned long long o = __shfl_xor_sync(0xffffffffu, best, 1);
+          best = o < best ? o : best;
+          o = __shfl_xor_sync(0xffffffffu, best, 2);
+          best = o < best ? o : best;
+          if (cg == 0 && rI[i] < rows) atomicMin(ckey + rI[i], best);
         }
       }
-      bestd[warp * 32 + lane] = bd; bestk[warp * 32 + lane] = bk;
-      __syncthreads();
-      if (sub == 0 && valid) {
-        for (int g2 = 1; g2 < G; ++g2) {
-          const float od = bestd[(warp + g2) * 32 + lane]; const int ok = bestk[(warp + g2) * 32 + lane];
-          if (cand_better(od, ok, bd, bk)) { bd = od; bk = ok; }
-        }
-        ckey[r] = cand_key(bd, bk);
-      }
+      if (s == 0) VQ_STAMP(41);
     }
+    VQ_STAMP(1 + s * 8 + 1);
     cluster.sync();                                   // all 8 slices of this row block have their candidates
+    VQ_STAMP(1 + s * 8 + 2);
     for (int r = tid; r < rows; r += NT) {
       unsigned long long best = ~0ull;
 #pragma unroll
@@ -552,9 +609,10 @@ rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
     }
 
     float n_stage = 0.f;
+    VQ_STAMP(1 + s * 8 + 3);
     if (a.training_ema) {
-      grid_barrier(barrier, generation, nblocks);     // the statistics of stage s are complete (also orders ckey reuse)
-      if (s > 0) update_stage(s - 1, n_prev);         // nobody reads stage s-1's old state any more
+      grid_barrier(barrier, generation, nblocks);
+      VQ_STAMP(1 + s * 8 + 4);     // the statistics of stage s are complete (also orders ckey reuse)
       {
         const float* cs = a.cs[s];
         double part = 0.0;
@@ -567,7 +625,7 @@ rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
         if (lane == 0) red[warp] = part;
         __syncthreads();
         if (tid < 32) {
-          double v = tid < 8 ? red[tid] : 0.0;
+          double v = tid < NW ? red[tid] : 0.0;
           v = warp_sum(v);
           if (tid == 0) s_n = (float)v;
         }
@@ -578,39 +636,53 @@ rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
       cluster.sync();                                 // eval / standard VQ: only ckey reuse needs ordering
     }
 
+    VQ_STAMP(1 + s * 8 + 5);
     // ---- gather (post-update codeword), straight-through value, loss sum, running sum, next residual ----
     float part = 0.f;
     {
-      constexpr int U = 4;
-      const float* Eg = a.E[s];
-      for (int i0 = tid; i0 < rows * D; i0 += NT * U) {
-        float q[U]; int ri[U];
+      // one item = 4 consecutive dims of one row (rows <= 64 -> at most NT * 4 items: a single batch); the codeword
+      // pieces of every item are requested before the first one is used
+      constexpr int U = 1024 / NT;
+      const int items = rows * (D / 4);
+      const float4* Eg4 = reinterpret_cast<const float4*>(a.E[s]);
+      const float4* dw4 = reinterpret_cast<const float4*>(dw);
+      const float4* w4 = reinterpret_cast<const float4*>(a.w[s]);
+      float4 wv[U], dv[U]; float clv[U]; int rr[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = i0 + u * NT;
-          if (i < rows * D) {
-            const int r = i / D, c = i - r * D;
-            ri[u] = r * LDR + c;
-            const int k = rowk[r];
-            if (a.training_ema) {
-              const float cl = __fmul_rn(__fdiv_rn(__fadd_rn(csn[k], a.eps), __fadd_rn(n_stage, a.k_eps[s])), n_stage);
-              const float wn = fmaf(__ldcg(dw + (size_t)k * D + c), a.one_minus_decay,
-                                    __fmul_rn(__ldcg(a.w[s] + (size_t)k * D + c), a.decay));
-              q[u] = __fdiv_rn(wn, cl);
-            } else {
-              q[u] = __ldcg(Eg + (size_t)k * D + c);
-            }
-          } else { ri[u] = -1; q[u] = 0.f; }
+      for (int u = 0; u < U; ++u) {
+        const int it = tid + u * NT;
+        rr[u] = -1; clv[u] = 1.f;
+        wv[u] = make_float4(0.f, 0.f, 0.f, 0.f); dv[u] = wv[u];
+        if (it < items) {
+          const int r = it / (D / 4), qd = it - r * (D / 4);
+          const int k = rowk[r];
+          rr[u] = r * LDR + 4 * qd;
+          if (a.training_ema) {
+            dv[u] = __ldcg(dw4 + (size_t)k * (D / 4) + qd);
+            wv[u] = __ldcg(w4 + (size_t)k * (D / 4) + qd);
+            clv[u] = __fmul_rn(__fdiv_rn(__fadd_rn(csn[k], a.eps), __fadd_rn(n_stage, a.k_eps[s])), n_stage);
+          } else {
+            wv[u] = __ldcg(Eg4 + (size_t)k * (D / 4) + qd);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (rr[u] < 0) continue;
+        float q[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
+        if (a.training_ema) {
+          const float d[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) q[e] = __fdiv_rn(fmaf(d[e], a.one_minus_decay, __fmul_rn(q[e], a.decay)), clv[u]);
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (ri[u] < 0) continue;
-          const float x = R[ri[u]];
-          const float diff = __fsub_rn(q[u], x);
+        for (int e = 0; e < 4; ++e) {
+          const float x = R[rr[u] + e];
+          const float diff = __fsub_rn(q[e], x);
           const float st = __fadd_rn(x, diff);
           part = fmaf(diff, diff, part);
-          O[ri[u]] = __fadd_rn(O[ri[u]], st);
-          R[ri[u]] = __fsub_rn(x, st);
+          O[rr[u] + e] = __fadd_rn(O[rr[u] + e], st);
+          R[rr[u] + e] = __fsub_rn(x, st);
         }
       }
     }
@@ -620,13 +692,15 @@ rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
       if (lane == 0) red[warp] = p;
       __syncthreads();
       if (tid < 32 && slice == 0) {                   // every slice computed the same sum: one of them reports it
-        double v = tid < 8 ? red[tid] : 0.0;
+        double v = tid < NW ? red[tid] : 0.0;
         v = warp_sum(v);
         if (tid == 0 && v != 0.0) atomicAdd(a.sse + s, v);
       }
     }
     __syncthreads();
-    n_prev = n_stage;
+#pragma unroll
+    for (int i = 0; i < small::MAX_S; ++i) if (i == s) n_of[i] = n_stage;
+    VQ_STAMP(1 + s * 8 + 6);
   }
 
   // ---- output: the row block's rows are dealt to the 8 CTAs of the cluster ----
@@ -638,41 +712,101 @@ rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
     a.out[(b * C + c) * T + t] = O[r * LDR + c];
   }
   grid_barrier(barrier, generation, nblocks);
-  if (a.training_ema) update_stage(a.S - 1, n_prev);
+  VQ_STAMP(61);
+  // every CTA has gathered with every stage's pre-update state: the in-place updates of ALL stages run here, off the
+  // per-stage critical path, as one flattened pass (a single L2 round trip instead of one per stage).  Stage sp's codes
+  // are split evenly over the CTAs; item = one float4 of one code.
+  if (a.training_ema) {
+    int ioff[small::MAX_S + 1];
+    ioff[0] = 0;
+#pragma unroll
+    for (int sp = 0; sp < small::MAX_S; ++sp) {
+      int cnt_codes = 0;
+      if (sp < a.S) {
+        const int per = (a.K[sp] + (int)nblocks - 1) / (int)nblocks;
+        const int k0 = min(a.K[sp], cta * per);
+        cnt_codes = min(a.K[sp], k0 + per) - k0;
+      }
+      ioff[sp + 1] = ioff[sp] + cnt_codes * (D / 4);
+    }
+    for (int it = tid; it < ioff[a.S]; it += NT) {
+      int sp = 0;
+#pragma unroll
+      for (int q = 1; q < small::MAX_S; ++q) sp += (q < a.S && it >= ioff[q]) ? 1 : 0;
+      const int Kp = a.K[sp];
+      const float* dwp = a.stats + stats_offset(a, sp);
+      const float* cntp = dwp + (long long)Kp * D;
+      const int per = (Kp + (int)nblocks - 1) / (int)nblocks;
+      const int k0 = min(Kp, cta * per);
+      const int i = it - ioff[sp];
+      const int k = k0 + i / (D / 4);
+      const float n = n_of[sp];
+      const size_t q4 = (size_t)k0 * (D / 4) + i;
+      const float4 d0 = __ldcg(reinterpret_cast<const float4*>(dwp) + q4);
+      const float4 w0 = __ldcg(reinterpret_cast<const float4*>(a.w[sp]) + q4);
+      const float csv = fmaf(__ldcg(cntp + k), a.one_minus_decay, __fmul_rn(__ldcg(a.cs[sp] + k), a.decay));
+      const float cl = __fmul_rn(__fdiv_rn(__fadd_rn(csv, a.eps), __fadd_rn(n, a.k_eps[sp])), n);
+      float4 n0;
+      n0.x = fmaf(d0.x, a.one_minus_decay, __fmul_rn(w0.x, a.decay)); n0.y = fmaf(d0.y, a.one_minus_decay, __fmul_rn(w0.y, a.decay));
+      n0.z = fmaf(d0.z, a.one_minus_decay, __fmul_rn(w0.z, a.decay)); n0.w = fmaf(d0.w, a.one_minus_decay, __fmul_rn(w0.w, a.decay));
+      reinterpret_cast<float4*>(a.w[sp])[q4] = n0;
+      reinterpret_cast<float4*>(a.E[sp])[q4] = make_float4(__fdiv_rn(n0.x, cl), __fdiv_rn(n0.y, cl), __fdiv_rn(n0.z, cl), __fdiv_rn(n0.w, cl));
+    }
+    __syncthreads();                                  // every thread has read the old cluster sizes of this CTA's codes
+    for (int it = tid; it < ioff[a.S] / (D / 4); it += NT) {
+      int sp = 0;
+#pragma unroll
+      for (int q = 1; q < small::MAX_S; ++q) sp += (q < a.S && it >= ioff[q] / (D / 4)) ? 1 : 0;
+      const int Kp = a.K[sp];
+      const float* cntp = a.stats + stats_offset(a, sp) + (long long)Kp * D;
+      const int per = (Kp + (int)nblocks - 1) / (int)nblocks;
+      const int k = min(Kp, cta * per) + (it - ioff[sp] / (D / 4));
+      a.cs[sp][k] = fmaf(__ldcg(cntp + k), a.one_minus_decay, __fmul_rn(__ldcg(a.cs[sp] + k), a.decay));
+    }
+  }
+  VQ_STAMP(62);
 
-  // ---- loss / perplexity / dcr of every stage (CTA 0, one warp per stage) ----
-  if (cta == 0 && warp < a.S) {
-    const int s = warp;
+  // ---- loss / perplexity / dcr: CTA s reports stage s (all threads, one block reduction) ----
+  if (cta < a.S) {
+    const int s = cta;
     const int K = a.K[s];
     const float* cnt = a.stats + stats_offset(a, s) + (long long)K * D;
     const float Nf = (float)N;
+    const double sse_s = (tid == 0) ? __ldcg(a.sse + s) : 0.0;
     double ent = 0.0; int active = 0;
-    for (int k0 = 0; k0 < K; k0 += 32 * 8) {
-      float c8[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { const int k = k0 + u * 32 + lane; c8[u] = (k < K) ? __ldcg(cnt + k) : 0.f; }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float p = __fdiv_rn(c8[u], Nf);
-        ent += (double)__fmul_rn(p, logf(__fadd_rn(p, 1e-10f)));
-        active += (c8[u] > 0.f);
-      }
+    for (int k = tid; k < K; k += NT) {
+      const float c1 = __ldcg(cnt + k);
+      const float p = __fdiv_rn(c1, Nf);
+      ent += (double)__fmul_rn(p, logf(__fadd_rn(p, 1e-10f)));
+      active += (c1 > 0.f);
     }
     ent = warp_sum(ent);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) active += __shfl_xor_sync(0xffffffffu, active, o);
-    if (lane == 0) {
-      const float mse = (float)(__ldcg(a.sse + s) / ((double)N * D));
+    __shared__ int red_i[NW];
+    if (lane == 0) { red[warp] = ent; red_i[warp] = active; }
+    __syncthreads();
+    if (tid == 0) {
+      double e = 0.0; int act = 0;
+      for (int w = 0; w < NW; ++w) { e += red[w]; act += red_i[w]; }
+      const float mse = (float)(sse_s / ((double)N * D));
       a.m3[s * 3 + 0] = a.use_ema ? __fmul_rn(a.commitment, mse) : __fadd_rn(mse, __fmul_rn(a.commitment, mse));
-      a.m3[s * 3 + 1] = expf(-(float)ent);
-      a.m3[s * 3 + 2] = __fsub_rn(1.0f, __fdiv_rn((float)active, (float)K));
+      a.m3[s * 3 + 1] = expf(-(float)e);
+      a.m3[s * 3 + 2] = __fsub_rn(1.0f, __fdiv_rn((float)act, (float)K));
     }
+  }
+  __syncthreads();
+  VQ_STAMP(63);
+  if (a.stamps && blockIdx.x == 0 && threadIdx.x == 0) {
+    printf("rvq_wide: %lld SM cycles in %llu ns; stamps (ns since stamp 0):", (long long)(clock64() - cyc0), gtime() - stamp[0]);
+    for (int i = 1; i < 64; ++i) if (stamp[i]) printf(" [%d]=%llu", i, stamp[i] - stamp[0]);
+    printf("\n");
   }
   cluster.sync();                                     // no CTA exits while its shared memory may still be read
 }
 
-constexpr size_t SMEM_BYTES = ((size_t)2 * MAX_RPB * LDR + (size_t)MAX_SLICE_CODES * (D + 1) + small::MAX_K + 8 * 32) * sizeof(float) +
-                              (8 * 32 + MAX_RPB) * sizeof(int) + MAX_RPB * sizeof(unsigned long long) + 16;
+constexpr size_t SMEM_BYTES = ((size_t)2 * MAX_RPB * LDR + (size_t)MAX_SLICE_CODES * (LDE + 1) + small::MAX_K + MAX_RPB) * sizeof(float) +
+                              MAX_RPB * sizeof(int) + MAX_RPB * sizeof(unsigned long long) + 16;
 
 }  // namespace wide
 }  // namespace vqb200
@@ -716,6 +850,7 @@ int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, in
     a.cs[s] = train_ema ? ema_cluster_size[s] : nullptr;
     a.w[s] = train_ema ? ema_w[s] : nullptr;
     VQ_CHECK_ARG(!train_ema || (a.cs[s] && a.w[s]), VQB200_EINVAL, "rvq_small_forward: EMA buffers of stage %d missing", s);
+    VQ_CHECK_ARG(!train_ema || (reinterpret_cast<uintptr_t>(a.w[s]) & 15) == 0, VQB200_EALIGN, "rvq_small_forward: ema_w %d must be 16-byte aligned", s);
     a.K[s] = (int)K[s];
     a.k_eps[s] = (float)((double)K[s] * eps);
     stats_floats += (size_t)stage_stats_floats(K[s]);
@@ -725,6 +860,8 @@ int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, in
   a.stats = workspace;
   a.scratch = workspace + ((stats_floats + 3) & ~(size_t)3);
   a.sse = sse; a.idx = idx; a.out = out; a.m3 = m3;
+  static const int stamps = [] { const char* e = getenv("VQB200_RVQ_STAMPS"); return e ? atoi(e) : 0; }();
+  a.stamps = stamps;
 
   // ---- wide variant: the whole GPU instead of one GPC (see namespace wide) ----
   {
@@ -755,6 +892,8 @@ int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, in
       int nc = 0;
       if (cudaOccupancyMaxActiveClusters(&nc, wide::rvq_wide_kernel, &q) != cudaSuccess) { cudaGetLastError(); nc = 0; }
       max_rb = nc > wide::MAX_RB ? wide::MAX_RB : (nc < 0 ? 0 : nc);
+      if (const char* e = getenv("VQB200_RVQ_WIDE_MAXRB")) max_rb = std::min(max_rb, atoi(e));     // development knob
+      if (getenv("VQB200_RVQ_WIDE_VERBOSE")) fprintf(stderr, "vqb200: rvq_wide: %d co-resident 8-CTA clusters, using up to %d\n", nc, max_rb);
       probe.store(2 + (size_t)max_rb);
     }
     if (!wide_off && coop == 1 && max_rb >= 4 && B * T <= (long long)max_rb * wide::MAX_RPB &&
@@ -776,7 +915,16 @@ int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, in
       attr[0].val.clusterDim.x = wide::CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       attr[1].id = cudaLaunchAttributeCooperative;
       attr[1].val.cooperative = 1;
-      cfg.attrs = attr; cfg.numAttrs = 2;
+      // Nsight Compute (2025.2) cannot launch a kernel that is both cooperative and clustered (the launch fails inside
+      // the tool).  Under an injected profiler kernels are serialised, so the co-residency the cooperative attribute
+      // guarantees follows from the occupancy probe above: launch the same kernel without the attribute there.
+      static const bool injected = [] {
+        const char* f = getenv("VQB200_RVQ_WIDE_NONCOOP");
+        if (f) return atoi(f) != 0;
+        return getenv("CUDA_INJECTION64_PATH") != nullptr || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr ||
+               getenv("NV_NSIGHT_INJECTION_PORT_BASE") != nullptr;
+      }();
+      cfg.attrs = attr; cfg.numAttrs = injected ? 1 : 2;
       VQ_CUDA(cudaLaunchKernelEx(&cfg, wide::rvq_wide_kernel, a, barrier));
       VQ_LAUNCH_CHECK("rvq_wide_kernel");
       return VQB200_OK;

@@ -29,7 +29,10 @@ rows = list(csv.reader(io.StringIO(src)))
 hi = next((i for i, r in enumerate(rows) if r and r[0] == "Address"), None)
 if hi is not None:
     hdr = rows[hi]
-    ci, cs, cx = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
+    cs_name = "# Samples" if "# Samples" in hdr else next((h for h in hdr if "Samples" in h), None)
+    if cs_name is None:
+        raise SystemExit(0)
+    ci, cs, cx = hdr.index("Source"), hdr.index(cs_name), hdr.index("Instructions Executed")
     stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
     data = []
     for r in rows[hi + 1:]:
