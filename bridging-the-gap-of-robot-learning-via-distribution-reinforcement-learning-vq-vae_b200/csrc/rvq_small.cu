@@ -334,6 +334,13 @@ rvq_small_kernel(const Args a) {
     }
   }
   __syncthreads();
+  if (rank == 0 && tid == 0) {                        // row S: sum of the stage losses, mean perplexity, mean dcr
+    float l = 0.f, p = 0.f, d = 0.f;
+    for (int s = 0; s < a.S; ++s) { l = __fadd_rn(l, a.m3[s * 3]); p = __fadd_rn(p, a.m3[s * 3 + 1]); d = __fadd_rn(d, a.m3[s * 3 + 2]); }
+    a.m3[a.S * 3 + 0] = l;
+    a.m3[a.S * 3 + 1] = __fdiv_rn(p, (float)a.S);
+    a.m3[a.S * 3 + 2] = __fdiv_rn(d, (float)a.S);
+  }
 }
 
 }  // namespace small
@@ -793,6 +800,18 @@ rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
       a.m3[s * 3 + 0] = a.use_ema ? __fmul_rn(a.commitment, mse) : __fadd_rn(mse, __fmul_rn(a.commitment, mse));
       a.m3[s * 3 + 1] = expf(-(float)e);
       a.m3[s * 3 + 2] = __fsub_rn(1.0f, __fdiv_rn((float)act, (float)K));
+      // the last of the S reporting CTAs adds row S: sum of the stage losses, mean perplexity, mean dcr
+      __threadfence();
+      if (atomicAdd(barrier + 1, 1u) == (unsigned)a.S - 1u) {
+        __threadfence();
+        float l = 0.f, p = 0.f, d = 0.f;
+        for (int q = 0; q < a.S; ++q) {
+          l = __fadd_rn(l, __ldcg(a.m3 + q * 3)); p = __fadd_rn(p, __ldcg(a.m3 + q * 3 + 1)); d = __fadd_rn(d, __ldcg(a.m3 + q * 3 + 2));
+        }
+        a.m3[a.S * 3 + 0] = l;
+        a.m3[a.S * 3 + 1] = __fdiv_rn(p, (float)a.S);
+        a.m3[a.S * 3 + 2] = __fdiv_rn(d, (float)a.S);
+      }
     }
   }
   __syncthreads();

@@ -150,7 +150,7 @@ class _RVQFn(torch.autograd.Function):
         N = B * T
         f32 = dict(dtype=torch.float32, device=dev)
         idx = torch.empty((S, B, T), dtype=torch.int32, device=dev)
-        m3 = torch.empty((S, 3), **f32)
+        m3 = torch.empty((S + 1, 3), **f32)          # row S: aggregate written by the single-launch kernels
         out = torch.empty((B, C, T), **f32)
         residuals = [z] + [torch.empty((B, C, T), **f32) for _ in range(S - 1)]
         ema_train = cfg.training and cfg.use_ema
@@ -267,12 +267,15 @@ class _RVQFn(torch.autograd.Function):
                     check(lib.vqb200_vq_metrics(ptr(st.cnt), weights[s].shape[0], max(N * world, 1), ptr(sse[s:s + 1]),
                                                 max(N * C, 1), c_float(cfg.commitment_cost), 1 if cfg.use_ema else 0,
                                                 ptr(m3[s]), stream), "vq_metrics")
-        if S == 1:
+        if fused:                       # the single-launch kernel has already reduced over the stages (row S)
+            loss, ppl, dcr = m3[S, 0], m3[S, 1], m3[S, 2]
+        elif S == 1:
             loss, ppl, dcr = m3[0, 0], m3[0, 1], m3[0, 2]
             if not cfg.plain:
-                ppl, dcr = m3[:, 1].mean(), m3[:, 2].mean()
+                ppl, dcr = m3[:S, 1].mean(), m3[:S, 2].mean()
         else:
-            loss, ppl, dcr = m3[:, 0].sum(), m3[:, 1].mean(), m3[:, 2].mean()
+            loss, ppl, dcr = m3[:S, 0].sum(), m3[:S, 1].mean(), m3[:S, 2].mean()
+        m3 = m3[:S]
         ctx.cfg = cfg
         ctx.S = S
         ctx.shape = (B, C, T)
@@ -467,7 +470,9 @@ class _ProjFusedFn(torch.autograd.Function):
                                                    ptr(_unique_workspace(dev)), ptr(m), stream_ptr(dev)), "fsq_fused_forward")
         ctx.save_for_backward(z, z_e, wi, wo)
         ctx.is_lfq, ctx.weight = bool(is_lfq), float(weight)
-        loss = m[0] if is_lfq else torch.zeros((), dtype=torch.float32, device=dev)
+        # FSQ has no loss term (models/vqvae.py:137): the module returns its own constant 0; this slot is an unused,
+        # uninitialised placeholder (no fill kernel)
+        loss = m[0] if is_lfq else m.new_empty(())
         ctx.mark_non_differentiable(idx, m, z_e)
         return out, loss, idx, m, z_e
 

@@ -13,7 +13,7 @@ import torch
 
 class GraphedQuantizerStep:
     """step(z, g) -> (loss, quantized, metrics, grad_z); all returned tensors are static buffers that the next
-    call overwrites.  `module` keeps its normal semantics (EMA buffers advance on every replay in train mode)."""
+    call overwrites, and so are the parameters' `.grad` (each replay overwrites them: zero_grad(set_to_none) semantics).  `module` keeps its normal semantics (EMA buffers advance on every replay in train mode)."""
 
     def __init__(self, module: torch.nn.Module, example_z: torch.Tensor, with_backward: bool = True, warmup: int = 3):
         if not example_z.is_cuda:
@@ -55,6 +55,10 @@ class GraphedQuantizerStep:
         loss, q, met = self.module(self.z)
         if self.with_backward:
             self.z.grad = None
+            # like optimizer.zero_grad(set_to_none=True): every replay WRITES the parameter gradients (into buffers of
+            # the graph's pool) instead of accumulating into older ones -- five fewer add kernels per Hybrid step
+            for p in self.module.parameters():
+                p.grad = None
             torch.autograd.backward([q, loss], [self.g, self._one])
         return loss, q, met
 

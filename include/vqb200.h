@@ -181,7 +181,8 @@ int vqb200_rvq_output_chain(const float* z, int64_t B, int64_t C, int64_t T,
  * only (no inter-GPU all-reduce inside the launch).  E / ema_cluster_size / ema_w / K are HOST arrays of S device
  * pointers / sizes; codebooks and EMA buffers are updated in place when training && use_ema.
  * workspace: vqb200_rvq_small_workspace_floats(S, K) floats (16-byte aligned); sse: S doubles;
- * idx: int32 [S, N]; out: contiguous [B,C,T]; m3: [S,3] = {loss, perplexity, dcr} per stage.
+ * idx: int32 [S, N]; out: contiguous [B,C,T]; m3: [S+1,3] = {loss, perplexity, dcr} per stage;
+ * row S = {sum of the stage losses, mean perplexity, mean dcr} (what ResidualVQ.forward returns, :104-108).
  * Derived codebook state (|E|^2, tile image) is NOT refreshed: call vqb200_codebook_prepare before the next
  * vqb200_vq_assign on these codebooks. */
 int    vqb200_rvq_small_eligible(int64_t N, int64_t D, int32_t S, const int64_t* K);
