@@ -55,6 +55,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--synthetic", type=int, default=0,
                    help="if > 0 and the .npy files are missing: train on N synthetic windows (rng seed 0)")
     p.add_argument("--exchange", type=str, default="auto", choices=["auto", "peer", "nccl"])
+    p.add_argument("--cuda_graph", action="store_true",
+                   help="single GPU: capture forward + backward + AdamW of a full batch in one CUDA graph and replay it")
     p.add_argument("--log_dir", type=str, default="results")
     p.add_argument("--ckpt_dir", type=str, default="checkpoints")
     return p
@@ -163,25 +165,92 @@ def train_one_seed(args, seed: int, device: torch.device, model_factory=None) ->
                 p.requires_grad = False
 
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=LR, weight_decay=WEIGHT_DECAY)
+    use_graph = bool(getattr(args, "cuda_graph", False)) and world == 1
+    # fused=True: one multi-tensor kernel for all ~160 parameters instead of several tiny kernels per parameter (same update
+    # rule as the reference's torch.optim.AdamW(lr=2e-4, weight_decay=1e-4), scripts/train_ablation.py:182)
+    opt = torch.optim.AdamW(params, lr=LR, weight_decay=WEIGHT_DECAY, capturable=use_graph, fused=True)
+
+    def forward_loss(x_r, x_h):
+        if args.mode == "teacher":
+            return teacher_loss(model(x_robot=x_r, x_human=None)["robot"], x_r)
+        out = model(x_robot=x_r, x_human=x_h)
+        return W_ALIGN * F.mse_loss(out["human"]["z_e"], out["robot"]["z_e"].detach())
+
+    graph = None
+    if use_graph:
+        # Whole-step CUDA graph: forward + backward + AdamW of one full batch captured once and
+        # replayed -- at batch 512 the transformer teacher is launch-bound end to end.  Every vqb200 call is
+        # capturable (no host sync, metrics stay on the device).  Only full batches replay; the ragged tail of an epoch is
+        # dropped.  Warm-up runs on a side stream and is rolled back so that the trajectory starts from the same state.
+        model.train()
+        xr_s = torch.empty((args.batch_size,) + tuple(x_r_all.shape[1:]), device=device)
+        xh_s = torch.empty((args.batch_size,) + tuple(x_h_all.shape[1:]), device=device)
+        first = torch.from_numpy(train_idx[:args.batch_size] if len(train_idx) >= args.batch_size else
+                                 np.resize(train_idx, args.batch_size)).to(device)
+        xr_s.copy_(x_r_all[first]); xh_s.copy_(x_h_all[first])
+        saved_model = {k: v.clone() for k, v in model.state_dict().items()}
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                opt.zero_grad(set_to_none=True)
+                forward_loss(xr_s, xh_s).backward()
+                opt.step()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        with torch.no_grad():
+            model.load_state_dict(saved_model)
+            for st_ in opt.state.values():          # Adam moments and step counters back to zero
+                for v in st_.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+        for m_ in model.modules():
+            if hasattr(m_, "invalidate_cache"):
+                m_.invalidate_cache()
+        opt.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss_s = forward_loss(xr_s, xh_s)
+            loss_s.backward()
+            opt.step()
+        with torch.no_grad():                       # capture does not execute, but be explicit about the state
+            model.load_state_dict(saved_model)
+        for m_ in model.modules():
+            if hasattr(m_, "invalidate_cache"):
+                m_.invalidate_cache()
+
     stale = 0
     t0 = time.time()
+    train_one_seed.step_ms = []                  # wall ms per training step of every epoch (tools/train_step_time.py)
     for epoch in range(start_epoch, args.epochs):
         model.train()
-        total, batches = 0.0, epoch_batches(train_idx, global_batch, seed, epoch)
+        batches = epoch_batches(train_idx, global_batch, seed, epoch)
+        if graph is not None:
+            batches = [b for b in batches if len(b) == args.batch_size]
+        total_t = torch.zeros((), dtype=torch.float64, device=device)        # no host sync inside the epoch
+        t_epoch = time.time()
         for gb in batches:
-            mine = torch.from_numpy(_shard(gb)).to(device)
+            mine = torch.from_numpy(_shard(gb)).to(device, non_blocking=True)
+            if graph is not None:
+                torch.index_select(x_r_all, 0, mine, out=xr_s)
+                torch.index_select(x_h_all, 0, mine, out=xh_s)
+                graph.replay()
+                total_t += loss_s.detach()
+                continue
             x_r, x_h = x_r_all[mine], x_h_all[mine]
             opt.zero_grad(set_to_none=True)
-            if args.mode == "teacher":
-                loss = teacher_loss(model(x_robot=x_r, x_human=None)["robot"], x_r)
-            else:
-                out = model(x_robot=x_r, x_human=x_h)
-                loss = W_ALIGN * F.mse_loss(out["human"]["z_e"], out["robot"]["z_e"].detach())
+            loss = forward_loss(x_r, x_h)
             loss.backward()
             vq_dist.average_gradients(params)
             opt.step()
-            total += float(loss.detach())
+            total_t += loss.detach()
+        total = float(total_t)                     # the epoch's only host sync
+        train_one_seed.step_ms.append((time.time() - t_epoch) * 1e3 / max(len(batches), 1))
+        if graph is not None:
+            # replays change weights behind Python's back (no tensor version bump): drop the codebook-derived caches
+            for m_ in model.modules():
+                if hasattr(m_, "invalidate_cache"):
+                    m_.invalidate_cache()
         model.eval()
         v_sum, v_cnt = 0.0, 0
         with torch.no_grad():
