@@ -11,7 +11,7 @@
 //   3. apply decay, Laplace smoothing and the normalisation, refresh |E|^2 / the bf16 tile image, as ema.cu does.
 // Slots are double-buffered by epoch parity: a rank overwrites slot e%2 only after it has passed barrier e+1, and a
 // peer signals e+1 only after (stream order) its reads of epoch e have completed.
-// A peer that never arrives (dead rank) trips a 30 s device-side timeout that traps instead of hanging the GPU.
+// A peer that never arrives (dead rank) trips a 120 s device-side timeout that traps instead of hanging the GPU.
 #include <string.h>
 #include "codebook.cuh"
 
@@ -19,7 +19,7 @@ namespace vqb200 {
 namespace peer {
 
 constexpr int MAX_PEERS = VQB200_MAX_PEERS;
-constexpr unsigned long long TIMEOUT_NS = 30ull * 1000ull * 1000ull * 1000ull;
+constexpr unsigned long long TIMEOUT_NS = 120ull * 1000ull * 1000ull * 1000ull;   // rank skew at start-up can be many seconds
 
 struct Table {
   const float* stats[MAX_PEERS];   // the SAME slot on every rank (index = rank), mapped into this process
@@ -48,7 +48,7 @@ __device__ __forceinline__ void publish_and_wait(const Table& t, int tid) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
       if ((int)(v - t.epoch) >= 0) break;
       if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > TIMEOUT_NS) {
-        printf("vqb200: rank %d waited 30 s for the EMA statistics of rank %d (epoch %u, saw %u)\n", t.rank, tid, t.epoch, v);
+        printf("vqb200: rank %d waited 120 s for the EMA statistics of rank %d (epoch %u, saw %u)\n", t.rank, tid, t.epoch, v);
         __trap();
       }
     }

@@ -111,7 +111,7 @@ int vqb200_ema_finalize(const float* stats, float* ema_cluster_size, float* ema_
  * current epoch / rank p's flag words, as mapped into THIS process (own buffer for p == rank).
  * `epoch` increases by one per call on every rank (slot = epoch & 1); flags start at 0, so the
  * first epoch is 1.  cnt_out (K floats, may be NULL) receives the reduced counts for
- * vqb200_vq_metrics.  A peer that does not arrive within 30 s traps the kernel (loud, no hang). */
+ * vqb200_vq_metrics.  A peer that does not arrive within 120 s traps the kernel (loud, no hang). */
 #define VQB200_MAX_PEERS 16
 #define VQB200_PEER_HANDLE_BYTES 64
 int vqb200_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle);
