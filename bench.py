@@ -186,7 +186,7 @@ def run_gpu(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-        vqb200.dist.enable(peer=args.exchange)
+        vqb200.dist.enable(peer=args.exchange, uniform_shards=True)      # every rank runs the same shapes
     cfg = dict(WORKLOADS[args.workload])
     if args.windows:
         cfg["B"] = args.windows

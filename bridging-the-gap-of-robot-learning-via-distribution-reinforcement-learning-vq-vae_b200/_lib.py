@@ -62,6 +62,12 @@ _SIGNATURES = {
     "vqb200_rvq_small_forward": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                          ctypes.c_int32, _P, _P, _P, _P, c_double, c_double, c_float, c_int, c_int,
                                          _P, _P, _P, _P, _P, _P]),
+    "vqb200_rvq_small_peer_eligible": (c_int, [c_int64, c_int64, ctypes.c_int32, _P]),
+    "vqb200_rvq_small_stats_floats": (c_size_t, [ctypes.c_int32, _P]),
+    "vqb200_rvq_small_forward_peer": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                              ctypes.c_int32, _P, _P, _P, _P, c_double, c_double, c_float,
+                                              _P, _P, _P, _P, _P, _P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32,
+                                              c_int64, _P]),
     "vqb200_vq_metrics": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_float, c_int, _P, _P]),
     "vqb200_vq_backward_input": (c_int, [_P, c_int64, c_int64, c_int64,
                                          _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,

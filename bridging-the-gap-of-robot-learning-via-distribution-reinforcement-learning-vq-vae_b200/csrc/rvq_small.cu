@@ -46,6 +46,13 @@ struct Args {
   float* out;                                   // [B,C,T] contiguous
   float* m3;                                    // [S][3] loss, perplexity, dcr
   int stamps;                                   // development (VQB200_RVQ_STAMPS): CTA 0 prints per-phase globaltimer stamps
+  // data-parallel ranks of one node (wide kernel only; world == 1: stats_of[0] == stats): every rank's statistics slot
+  // and flag words as mapped into this process, the first barrier epoch of this call, vectors of ALL ranks
+  int world, rank, peer_timeout_s;
+  unsigned epoch0;
+  long long n_total;
+  const float* stats_of[VQB200_MAX_PEERS];
+  unsigned* flags_of[VQB200_MAX_PEERS];
 };
 
 // [dw (K*D) | cnt (K)] of one stage, padded so that every stage's dw stays 16-byte aligned (vector reductions)
@@ -392,6 +399,76 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& genera
   __syncthreads();
 }
 
+// statistics summed over the ranks in RANK ORDER (identical bits on every rank); off = float offset inside a slot
+__device__ __forceinline__ float sum_ranks(const Args& a, long long off) {
+  float v = __ldcg(a.stats_of[0] + off);
+  for (int p = 1; p < a.world; ++p) v = __fadd_rn(v, __ldcg(a.stats_of[p] + off));
+  return v;
+}
+__device__ __forceinline__ float4 sum_ranks4(const Args& a, long long off4) {      // off4 in float4 units
+  float4 v = __ldcg(reinterpret_cast<const float4*>(a.stats_of[0]) + off4);
+  for (int p = 1; p < a.world; ++p) {
+    const float4 o = __ldcg(reinterpret_cast<const float4*>(a.stats_of[p]) + off4);
+    v.x = __fadd_rn(v.x, o.x); v.y = __fadd_rn(v.y, o.y); v.z = __fadd_rn(v.z, o.z); v.w = __fadd_rn(v.w, o.w);
+  }
+  return v;
+}
+
+// Grid barrier that also spans the data-parallel ranks: every CTA arrives on the local counter; CTA 0 waits for all
+// local arrivals, publishes `epoch` into every peer's flag word over NVLink and waits for theirs (csrc/peer.cu
+// protocol), then releases the local CTAs through a second word.  world == 1 callers use grid_barrier().
+__device__ __forceinline__ void grid_barrier_world(const Args& a, unsigned* bar, unsigned& generation, unsigned nblocks,
+                                                   unsigned epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const unsigned target = (generation + 1u) * nblocks;
+    unsigned spins = 0;
+    if (blockIdx.x == 0) {
+      while (true) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        if (v >= target) break;
+        if (++spins > SPIN_LIMIT) { printf("vqb200 rvq_wide_kernel: local arrivals timed out (%u of %u)\n", v, target); __trap(); }
+      }
+      __threadfence_system();
+      for (int p = 0; p < a.world; ++p)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.flags_of[p] + a.rank), "r"(epoch) : "memory");
+      unsigned long long t0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      for (int p = 0; p < a.world; ++p) {
+        unsigned polls = 0;
+        while (true) {
+          unsigned v;
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flags_of[a.rank] + p) : "memory");
+          if ((int)(v - epoch) >= 0) break;
+          if ((++polls & 1023u) == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > (unsigned long long)a.peer_timeout_s * 1000000000ull) {
+              printf("vqb200 rvq_wide_kernel: rank %d waited %d s for rank %d (epoch %u, saw %u)\n", a.rank, a.peer_timeout_s, p, epoch, v);
+              __trap();
+            }
+          }
+        }
+      }
+      __threadfence_system();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(bar + 2), "r"(generation + 1u) : "memory");
+    }
+    spins = 0;
+    while (true) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar + 2) : "memory");
+      if (v >= generation + 1u) break;
+      if (++spins > (SPIN_LIMIT << 6)) { printf("vqb200 rvq_wide_kernel: release word timed out in CTA %d\n", (int)blockIdx.x); __trap(); }
+    }
+    __threadfence();
+  }
+  ++generation;
+  __syncthreads();
+}
+
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -618,13 +695,14 @@ rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
     float n_stage = 0.f;
     VQ_STAMP(1 + s * 8 + 3);
     if (a.training_ema) {
-      grid_barrier(barrier, generation, nblocks);
+      if (a.world > 1) grid_barrier_world(a, barrier, generation, nblocks, a.epoch0 + (unsigned)s);
+      else grid_barrier(barrier, generation, nblocks);
       VQ_STAMP(1 + s * 8 + 4);     // the statistics of stage s are complete (also orders ckey reuse)
       {
         const float* cs = a.cs[s];
         double part = 0.0;
         for (int k = tid; k < K; k += NT) {
-          const float v = fmaf(__ldcg(cnt + k), a.one_minus_decay, __fmul_rn(__ldcg(cs + k), a.decay));
+          const float v = fmaf(sum_ranks(a, stats_offset(a, s) + (long long)K * D + k), a.one_minus_decay, __fmul_rn(__ldcg(cs + k), a.decay));
           csn[k] = v;
           part += (double)v;
         }
@@ -652,7 +730,7 @@ rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
       constexpr int U = 1024 / NT;
       const int items = rows * (D / 4);
       const float4* Eg4 = reinterpret_cast<const float4*>(a.E[s]);
-      const float4* dw4 = reinterpret_cast<const float4*>(dw);
+      const long long dw4_off = stats_offset(a, s) / 4;
       const float4* w4 = reinterpret_cast<const float4*>(a.w[s]);
       float4 wv[U], dv[U]; float clv[U]; int rr[U];
 #pragma unroll
@@ -665,7 +743,7 @@ rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
           const int k = rowk[r];
           rr[u] = r * LDR + 4 * qd;
           if (a.training_ema) {
-            dv[u] = __ldcg(dw4 + (size_t)k * (D / 4) + qd);
+            dv[u] = sum_ranks4(a, dw4_off + (long long)k * (D / 4) + qd);
             wv[u] = __ldcg(w4 + (size_t)k * (D / 4) + qd);
             clv[u] = __fmul_rn(__fdiv_rn(__fadd_rn(csn[k], a.eps), __fadd_rn(n_stage, a.k_eps[s])), n_stage);
           } else {
@@ -741,17 +819,16 @@ rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
 #pragma unroll
       for (int q = 1; q < small::MAX_S; ++q) sp += (q < a.S && it >= ioff[q]) ? 1 : 0;
       const int Kp = a.K[sp];
-      const float* dwp = a.stats + stats_offset(a, sp);
-      const float* cntp = dwp + (long long)Kp * D;
+      const long long so = stats_offset(a, sp);
       const int per = (Kp + (int)nblocks - 1) / (int)nblocks;
       const int k0 = min(Kp, cta * per);
       const int i = it - ioff[sp];
       const int k = k0 + i / (D / 4);
       const float n = n_of[sp];
       const size_t q4 = (size_t)k0 * (D / 4) + i;
-      const float4 d0 = __ldcg(reinterpret_cast<const float4*>(dwp) + q4);
+      const float4 d0 = sum_ranks4(a, so / 4 + (long long)q4);
       const float4 w0 = __ldcg(reinterpret_cast<const float4*>(a.w[sp]) + q4);
-      const float csv = fmaf(__ldcg(cntp + k), a.one_minus_decay, __fmul_rn(__ldcg(a.cs[sp] + k), a.decay));
+      const float csv = fmaf(sum_ranks(a, so + (long long)Kp * D + k), a.one_minus_decay, __fmul_rn(__ldcg(a.cs[sp] + k), a.decay));
       const float cl = __fmul_rn(__fdiv_rn(__fadd_rn(csv, a.eps), __fadd_rn(n, a.k_eps[sp])), n);
       float4 n0;
       n0.x = fmaf(d0.x, a.one_minus_decay, __fmul_rn(w0.x, a.decay)); n0.y = fmaf(d0.y, a.one_minus_decay, __fmul_rn(w0.y, a.decay));
@@ -765,10 +842,9 @@ rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
 #pragma unroll
       for (int q = 1; q < small::MAX_S; ++q) sp += (q < a.S && it >= ioff[q] / (D / 4)) ? 1 : 0;
       const int Kp = a.K[sp];
-      const float* cntp = a.stats + stats_offset(a, sp) + (long long)Kp * D;
       const int per = (Kp + (int)nblocks - 1) / (int)nblocks;
       const int k = min(Kp, cta * per) + (it - ioff[sp] / (D / 4));
-      a.cs[sp][k] = fmaf(__ldcg(cntp + k), a.one_minus_decay, __fmul_rn(__ldcg(a.cs[sp] + k), a.decay));
+      a.cs[sp][k] = fmaf(sum_ranks(a, stats_offset(a, sp) + (long long)Kp * D + k), a.one_minus_decay, __fmul_rn(__ldcg(a.cs[sp] + k), a.decay));
     }
   }
   VQ_STAMP(62);
@@ -777,12 +853,12 @@ rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
   if (cta < a.S) {
     const int s = cta;
     const int K = a.K[s];
-    const float* cnt = a.stats + stats_offset(a, s) + (long long)K * D;
-    const float Nf = (float)N;
+    const long long cnt_off = stats_offset(a, s) + (long long)K * D;
+    const float Nf = (float)a.n_total;            // perplexity / dcr over the vectors of ALL ranks
     const double sse_s = (tid == 0) ? __ldcg(a.sse + s) : 0.0;
     double ent = 0.0; int active = 0;
     for (int k = tid; k < K; k += NT) {
-      const float c1 = __ldcg(cnt + k);
+      const float c1 = sum_ranks(a, cnt_off + k);
       const float p = __fdiv_rn(c1, Nf);
       ent += (double)__fmul_rn(p, logf(__fadd_rn(p, 1e-10f)));
       active += (c1 > 0.f);
@@ -846,11 +922,51 @@ size_t vqb200_rvq_small_workspace_floats(int32_t S, const int64_t* K) {
   return n + 16;
 }
 
-int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,
+}  // extern "C"
+
+namespace vqb200 {
+// number of co-resident 8-CTA clusters of the wide kernel on the current device (0: no cooperative launch / disabled)
+static int wide_row_blocks(int* out) {
+  static const int wide_off = [] { const char* e = getenv("VQB200_RVQ_SMALL_NARROW"); return e ? atoi(e) : 0; }();
+  // per device: 0 = not probed, 1 = no cooperative launch, 2 + n = n co-resident clusters (GPC floor-planning decides)
+  static PerDevice probe_;
+  std::atomic<size_t>& probe = probe_.here();
+  if (probe.load() == 0) {
+    int dev = 0, v = 0;
+    const bool coop = cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && v;
+    if (!coop) { cudaGetLastError(); probe.store(1); }
+    else {
+      VQ_CUDA(cudaFuncSetAttribute(wide::rvq_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide::SMEM_BYTES));
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(wide::MAX_RB * wide::CS); q.blockDim = dim3(wide::NT); q.dynamicSmemBytes = wide::SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = wide::CS; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, wide::rvq_wide_kernel, &q) != cudaSuccess) { cudaGetLastError(); nc = 0; }
+      int max_rb = nc > wide::MAX_RB ? wide::MAX_RB : (nc < 0 ? 0 : nc);
+      if (const char* e = getenv("VQB200_RVQ_WIDE_MAXRB")) max_rb = std::min(max_rb, atoi(e));     // development knob
+      if (getenv("VQB200_RVQ_WIDE_VERBOSE")) fprintf(stderr, "vqb200: rvq_wide: %d co-resident 8-CTA clusters, using up to %d\n", nc, max_rb);
+      probe.store(2 + (size_t)max_rb);
+    }
+  }
+  *out = (wide_off || probe.load() < 2) ? 0 : (int)probe.load() - 2;
+  return VQB200_OK;
+}
+
+static bool wide_shape_ok(int max_rb, long long N, int32_t S, const int64_t* K) {
+  long long slice_codes = 0;
+  for (int s = 0; s < S; ++s) slice_codes += (K[s] + wide::CS - 1) / wide::CS;
+  return max_rb >= 4 && N <= (long long)max_rb * wide::MAX_RPB && slice_codes <= wide::MAX_SLICE_CODES;
+}
+
+static int rvq_small_forward_impl(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,
                              int32_t S, float* const* E, float* const* ema_cluster_size, float* const* ema_w,
                              const int64_t* K, double decay, double eps, float commitment_cost, int use_ema,
                              int training, float* workspace, double* sse, int32_t* idx, float* out, float* m3,
-                             vqb200_stream_t stream_) {
+                             const float* const* peer_stats, uint32_t* const* peer_flags, int rank, int world,
+                             uint32_t epoch0, int64_t n_total, vqb200_stream_t stream_) {
   using namespace small;
   cudaStream_t stream = (cudaStream_t)stream_;
   VQ_CHECK_ARG(z && E && K && workspace && sse && idx && out && m3, VQB200_EINVAL, "rvq_small_forward: null pointer");
@@ -881,48 +997,39 @@ int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, in
   a.sse = sse; a.idx = idx; a.out = out; a.m3 = m3;
   static const int stamps = [] { const char* e = getenv("VQB200_RVQ_STAMPS"); return e ? atoi(e) : 0; }();
   a.stamps = stamps;
+  for (int p = 0; p < VQB200_MAX_PEERS; ++p) { a.stats_of[p] = nullptr; a.flags_of[p] = nullptr; }
+  a.world = 1; a.rank = 0; a.epoch0 = 0; a.n_total = B * T; a.stats_of[0] = a.stats;
+  static const int peer_timeout = [] { const char* e = getenv("VQB200_PEER_TIMEOUT_S"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 120; }();
+  a.peer_timeout_s = peer_timeout;
+  if (world > 1) {
+    VQ_CHECK_ARG(train_ema, VQB200_EINVAL, "rvq_small_forward_peer: only the EMA training step exchanges statistics");
+    VQ_CHECK_ARG(peer_stats && peer_flags && world <= VQB200_MAX_PEERS && rank >= 0 && rank < world, VQB200_ESHAPE,
+                 "rvq_small_forward_peer: bad rank %d / world %d", rank, world);
+    for (int p = 0; p < world; ++p) {
+      VQ_CHECK_ARG(peer_stats[p] && peer_flags[p] && (reinterpret_cast<uintptr_t>(peer_stats[p]) & 15) == 0, VQB200_EALIGN,
+                   "rvq_small_forward_peer: slot of rank %d missing or not 16-byte aligned", p);
+      a.stats_of[p] = peer_stats[p];
+      a.flags_of[p] = reinterpret_cast<unsigned*>(peer_flags[p]);
+    }
+    a.world = world; a.rank = rank; a.epoch0 = epoch0; a.n_total = n_total;
+    a.stats = const_cast<float*>(peer_stats[rank]);       // this rank accumulates straight into its own slot
+  }
 
   // ---- wide variant: the whole GPU instead of one GPC (see namespace wide) ----
   {
-    long long slice_codes = 0;
-    for (int s = 0; s < S; ++s) slice_codes += (K[s] + wide::CS - 1) / wide::CS;
-    static const int wide_off = [] { const char* e = getenv("VQB200_RVQ_SMALL_NARROW"); return e ? atoi(e) : 0; }();
-    // per device: 0 = not probed, 1 = no cooperative launch, 2 + n = n co-resident 8-CTA clusters (GPC floor-planning
-    // decides, not SMs / 8)
-    static PerDevice probe_;
-    std::atomic<size_t>& probe = probe_.here();
-    int coop = 0, max_rb = 0;
-    if (probe.load() == 0) {
-      int dev = 0, v = 0;
-      coop = (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && v) ? 1 : 0;
-      if (!coop) probe.store(1);
-    } else {
-      coop = probe.load() >= 2 ? 1 : 0;
-      max_rb = coop ? (int)probe.load() - 2 : 0;
-    }
-    if (coop == 1 && probe.load() == 0) {
-      VQ_CUDA(cudaFuncSetAttribute(wide::rvq_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide::SMEM_BYTES));
-      cudaLaunchConfig_t q = {};
-      q.gridDim = dim3(wide::MAX_RB * wide::CS); q.blockDim = dim3(wide::NT); q.dynamicSmemBytes = wide::SMEM_BYTES;
-      cudaLaunchAttribute qa[1];
-      qa[0].id = cudaLaunchAttributeClusterDimension;
-      qa[0].val.clusterDim.x = wide::CS; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-      q.attrs = qa; q.numAttrs = 1;
-      int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, wide::rvq_wide_kernel, &q) != cudaSuccess) { cudaGetLastError(); nc = 0; }
-      max_rb = nc > wide::MAX_RB ? wide::MAX_RB : (nc < 0 ? 0 : nc);
-      if (const char* e = getenv("VQB200_RVQ_WIDE_MAXRB")) max_rb = std::min(max_rb, atoi(e));     // development knob
-      if (getenv("VQB200_RVQ_WIDE_VERBOSE")) fprintf(stderr, "vqb200: rvq_wide: %d co-resident 8-CTA clusters, using up to %d\n", nc, max_rb);
-      probe.store(2 + (size_t)max_rb);
-    }
-    if (!wide_off && coop == 1 && max_rb >= 4 && B * T <= (long long)max_rb * wide::MAX_RPB &&
-        slice_codes <= wide::MAX_SLICE_CODES) {
+    int max_rb = 0;
+    { const int rc = wide_row_blocks(&max_rb); if (rc != VQB200_OK) return rc; }
+    const bool wide_ok = wide_shape_ok(max_rb, B * T, S, K);
+    VQ_CHECK_ARG(world == 1 || wide_ok, VQB200_EUNSUPPORTED,
+                 "rvq_small_forward_peer: only the whole-GPU variant runs under data parallelism (see vqb200_rvq_small_peer_eligible)");
+    if (wide_ok) {
       const int rb_used = (int)std::min<long long>(max_rb, (B * T + 15) / 16);            // at least 16 rows per block
       size_t scratch_floats = 0;
       for (int s = 0; s < S; ++s) scratch_floats += (size_t)K[s] + 8;
       unsigned* barrier = reinterpret_cast<unsigned*>(a.scratch + scratch_floats);       // inside the +16 slack
       const size_t zero_bytes = (size_t)((reinterpret_cast<unsigned char*>(barrier) + 16) - reinterpret_cast<unsigned char*>(workspace));
-      VQ_CUDA(cudaMemsetAsync(workspace, 0, zero_bytes, stream));                        // statistics + barrier counter
+      VQ_CUDA(cudaMemsetAsync(workspace, 0, zero_bytes, stream));                        // statistics + barrier words
+      if (world > 1) VQ_CUDA(cudaMemsetAsync(a.stats, 0, stats_floats * sizeof(float), stream));   // ... of the peer slot
       VQ_CUDA(cudaMemsetAsync(sse, 0, (size_t)S * sizeof(double), stream));
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((rb_used < 1 ? 1 : rb_used) * wide::CS);
@@ -971,6 +1078,42 @@ int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, in
   VQ_CUDA(cudaLaunchKernelEx(&cfg, rvq_small_kernel, a));
   VQ_LAUNCH_CHECK("rvq_small_kernel");
   return VQB200_OK;
+}
+}  // namespace vqb200
+
+extern "C" {
+
+int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,
+                             int32_t S, float* const* E, float* const* ema_cluster_size, float* const* ema_w,
+                             const int64_t* K, double decay, double eps, float commitment_cost, int use_ema,
+                             int training, float* workspace, double* sse, int32_t* idx, float* out, float* m3,
+                             vqb200_stream_t stream) {
+  return rvq_small_forward_impl(z, B, C, T, sB, sC, sT, S, E, ema_cluster_size, ema_w, K, decay, eps, commitment_cost, use_ema,
+                                training, workspace, sse, idx, out, m3, nullptr, nullptr, 0, 1, 0, B * T, stream);
+}
+
+int vqb200_rvq_small_peer_eligible(int64_t N, int64_t D, int32_t S, const int64_t* K) {
+  if (!vqb200_rvq_small_eligible(N, D, S, K)) return 0;
+  int max_rb = 0;
+  if (wide_row_blocks(&max_rb) != VQB200_OK) return 0;
+  return wide_shape_ok(max_rb, N, S, K) ? 1 : 0;
+}
+
+size_t vqb200_rvq_small_stats_floats(int32_t S, const int64_t* K) {
+  size_t n = 0;
+  for (int s = 0; s < S; ++s) n += (size_t)small::stage_stats_floats(K[s]);
+  return n;
+}
+
+int vqb200_rvq_small_forward_peer(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,
+                                  int32_t S, float* const* E, float* const* ema_cluster_size, float* const* ema_w,
+                                  const int64_t* K, double decay, double eps, float commitment_cost,
+                                  float* workspace, double* sse, int32_t* idx, float* out, float* m3,
+                                  const float* const* peer_stats, uint32_t* const* peer_flags, int32_t rank, int32_t world,
+                                  uint32_t epoch0, int64_t n_total, vqb200_stream_t stream) {
+  VQ_CHECK_ARG(world >= 1, VQB200_ESHAPE, "rvq_small_forward_peer: bad world %d", world);
+  return rvq_small_forward_impl(z, B, C, T, sB, sC, sT, S, E, ema_cluster_size, ema_w, K, decay, eps, commitment_cost, 1, 1,
+                                workspace, sse, idx, out, m3, peer_stats, peer_flags, rank, world, epoch0, n_total, stream);
 }
 
 }  // extern "C"

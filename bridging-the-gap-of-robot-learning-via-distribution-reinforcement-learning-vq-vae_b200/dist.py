@@ -34,6 +34,7 @@ _GROUP = None
 _ENABLED = False
 _PEER: Optional["PeerExchange"] = None
 _PEER_STATUS = "off"
+_UNIFORM = False
 
 FLAG_BYTES = 256                       # VQB200_MAX_PEERS x uint32, padded
 DEFAULT_SLOT_BYTES = 16 << 20          # K*(D+1)*4 per stage: 266 KB at 1024 x 64, 8.4 MB at 16384 x 128
@@ -53,6 +54,7 @@ class PeerExchange:
         self.world = torch_dist.get_world_size(group)
         self.slot_bytes = (int(slot_bytes) + 255) // 256 * 256
         self.epoch = 0
+        self.uses = 0
         self.base: List[int] = [0] * self.world
         self._opened: List[int] = []
         self._own = 0
@@ -113,11 +115,16 @@ class PeerExchange:
     def fits(self, K: int, D: int) -> bool:
         return K * (D + 1) * 4 <= self.slot_bytes
 
-    def next_slot(self):
-        """Advance the epoch; returns (epoch, device pointer of MY slot, table of every rank's slot)."""
-        self.epoch = (self.epoch + 1) & 0xFFFFFFFF
-        s = self.epoch & 1
-        return self.epoch, self._own + FLAG_BYTES + s * self.slot_bytes, self._slots[s]
+    def next_slot(self, n_epochs: int = 1):
+        """One use of the exchange: returns (first epoch, device pointer of MY slot, table of every rank's slot) and
+        consumes `n_epochs` barrier epochs (1 for a finalize call, S for a single-launch ResidualVQ).  Slots alternate
+        per USE: a rank overwrites a slot only after it has passed every barrier of the next use, and a peer signals
+        those only after (stream order) it finished reading this one."""
+        first = (self.epoch + 1) & 0xFFFFFFFF
+        self.epoch = (self.epoch + n_epochs) & 0xFFFFFFFF
+        self.uses += 1
+        s = self.uses & 1
+        return first, self._own + FLAG_BYTES + s * self.slot_bytes, self._slots[s]
 
     @property
     def flags(self):
@@ -149,10 +156,14 @@ def _device_uuid(device: torch.device) -> str:
 
 
 def enable(group=None, peer: str = "auto", device: Optional[torch.device] = None,
-           slot_bytes: int = DEFAULT_SLOT_BYTES) -> None:
+           slot_bytes: int = DEFAULT_SLOT_BYTES, uniform_shards: bool = False) -> None:
     """Turn on the per-stage EMA-statistics exchange (call after init_process_group; collective).
-    peer: "auto" | "peer" | "nccl" (see the module docstring).  `device` defaults to the current CUDA device."""
-    global _GROUP, _ENABLED, _PEER, _PEER_STATUS
+    peer: "auto" | "peer" | "nccl" (see the module docstring).  `device` defaults to the current CUDA device.
+    uniform_shards: the caller's promise that every rank feeds the quantizers tensors of the SAME shape in every
+    step; it lets launch-bound shapes take the single-launch ResidualVQ kernel with the exchange inside
+    (`vqb200_rvq_small_forward_peer`) -- a choice all ranks must make alike."""
+    global _GROUP, _ENABLED, _PEER, _PEER_STATUS, _UNIFORM
+    _UNIFORM = bool(uniform_shards)
     if not torch_dist.is_available() or not torch_dist.is_initialized():
         raise RuntimeError("vqb200.dist.enable(): torch.distributed is not initialised")
     if peer not in ("auto", "peer", "nccl"):
@@ -187,9 +198,13 @@ def _close_peer() -> None:
 
 
 def disable() -> None:
-    global _GROUP, _ENABLED, _PEER_STATUS
+    global _GROUP, _ENABLED, _PEER_STATUS, _UNIFORM
     _close_peer()
-    _GROUP, _ENABLED, _PEER_STATUS = None, False, "off"
+    _GROUP, _ENABLED, _PEER_STATUS, _UNIFORM = None, False, "off", False
+
+
+def uniform_shards() -> bool:
+    return _UNIFORM and enabled()
 
 
 def peer_exchange() -> Optional[PeerExchange]:

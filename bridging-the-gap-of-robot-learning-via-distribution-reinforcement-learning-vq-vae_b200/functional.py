@@ -166,6 +166,16 @@ class _RVQFn(torch.autograd.Function):
         fused = (cfg.algo == _lib.ASSIGN_AUTO and N > 0 and not _dist.enabled()
                  and (cfg.use_ema or not any(ctx.needs_input_grad[2:]))
                  and bool(lib.vqb200_rvq_small_eligible(N, C, S, Ks)))
+        # under data parallelism the single-launch kernel runs with the exchange inside (csrc/rvq_small.cu,
+        # grid_barrier_world) when the caller promised equal shards -- all ranks must choose alike
+        px = _dist.peer_exchange() if ema_train else None
+        fused_peer = False
+        if (not fused and cfg.algo == _lib.ASSIGN_AUTO and N > 0 and px is not None and px.device == dev
+                and _dist.uniform_shards()):
+            with torch.cuda.device(dev):
+                fused_peer = (bool(lib.vqb200_rvq_small_peer_eligible(N, C, S, Ks))
+                              and int(lib.vqb200_rvq_small_stats_floats(S, Ks)) * 4 <= px.slot_bytes)
+            fused = fused_peer
         if fused:
             with torch.cuda.device(dev):
                 stream = stream_ptr(dev)
@@ -184,10 +194,18 @@ class _RVQFn(torch.autograd.Function):
                     st0._small_ws = ws
                 sse = torch.empty(S, dtype=torch.float64, device=dev)
                 sB, sC, sT = z.stride()
-                check(lib.vqb200_rvq_small_forward(ptr(z), B, C, T, sB, sC, sT, S, Es, Cs, Ws, Ks, c_double(cfg.decay),
-                                                   c_double(cfg.eps), c_float(cfg.commitment_cost),
-                                                   1 if cfg.use_ema else 0, 1 if cfg.training else 0, ptr(ws), ptr(sse),
-                                                   ptr(idx), ptr(out), ptr(m3), stream), "rvq_small_forward")
+                if fused_peer:
+                    epoch0, _mine, slots = px.next_slot(S)
+                    check(lib.vqb200_rvq_small_forward_peer(ptr(z), B, C, T, sB, sC, sT, S, Es, Cs, Ws, Ks, c_double(cfg.decay),
+                                                            c_double(cfg.eps), c_float(cfg.commitment_cost), ptr(ws), ptr(sse),
+                                                            ptr(idx), ptr(out), ptr(m3), slots, px.flags, px.rank, px.world,
+                                                            ctypes.c_uint32(epoch0), N * px.world, stream),
+                          "rvq_small_forward_peer")
+                else:
+                    check(lib.vqb200_rvq_small_forward(ptr(z), B, C, T, sB, sC, sT, S, Es, Cs, Ws, Ks, c_double(cfg.decay),
+                                                       c_double(cfg.eps), c_float(cfg.commitment_cost),
+                                                       1 if cfg.use_ema else 0, 1 if cfg.training else 0, ptr(ws), ptr(sse),
+                                                       ptr(idx), ptr(out), ptr(m3), stream), "rvq_small_forward")
                 for s in range(S):
                     cfg.states[s].invalidate()      # |E|^2 / tile image were not refreshed by the fused kernel
                 if ema_train and ctx.needs_input_grad[0]:
@@ -217,7 +235,6 @@ class _RVQFn(torch.autograd.Function):
                                                         Wp.shape[0], ptr(r), ptr(W), ptr(st.ee), ptr(st.image),
                                                         ptr(st.info), K, ptr(idx[s]), ptr(ws), c_size_t(ws.numel()),
                                                         cfg.algo, stream), "vq_assign_residual")
-                px = _dist.peer_exchange() if ema_train else None
                 if ema_train and px is not None and px.device == dev and px.fits(K, D):
                     # K3a into this rank's slot of the symmetric buffer; K3b barriers and sums every rank's slot over
                     # NVLink itself (csrc/peer.cu): no collective launch between the two

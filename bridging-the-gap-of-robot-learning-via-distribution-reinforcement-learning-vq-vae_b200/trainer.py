@@ -91,6 +91,10 @@ def epoch_batches(train_idx: np.ndarray, global_batch: int, seed: int, epoch: in
     # every rank must take part in every training step (the EMA finalize kernels barrier across ranks): a trailing
     # batch with fewer samples than ranks is dropped
     world = vq_dist.world_size()
+    if vq_dist.uniform_shards():
+        # equal shards on every rank (the promise behind enable(uniform_shards=True)): trim each batch to a multiple of
+        # the world size -- at most world-1 samples of the ragged tail are skipped per epoch
+        out = [b[:len(b) // world * world] for b in out]
     return [b for b in out if len(b) >= world]
 
 
@@ -311,7 +315,7 @@ def main(argv: Optional[List[str]] = None) -> int:
         import torch.distributed as td
         if not td.is_initialized():
             td.init_process_group("nccl", device_id=device)
-        vq_dist.enable(peer=args.exchange)
+        vq_dist.enable(peer=args.exchange, uniform_shards=True)
         if vq_dist.rank() == 0:
             print(f"vqb200 trainer: {world} ranks, EMA statistics exchange = {vq_dist.peer_status()}", flush=True)
     try:

@@ -194,6 +194,31 @@ int vqb200_rvq_small_forward(const float* z, int64_t B, int64_t C, int64_t T,
                              int training, float* workspace, double* sse, int32_t* idx, float* out, float* m3,
                              vqb200_stream_t stream);
 
+/* ---- K4 under data parallelism: the single-launch ResidualVQ with the exchange inside ---------
+ * vqb200_rvq_small_forward for the EMA training step of data-parallel ranks of one node: the
+ * whole-GPU (cooperative) kernel accumulates each stage's statistics straight into this rank's
+ * peer slot (vqb200_peer_alloc above), and its per-stage grid barrier also spans the ranks --
+ * CTA 0 publishes epoch0 + s into every peer's flag word over NVLink and waits for theirs -- after
+ * which every CTA reads all ranks' [dw | cnt] over peer memory and sums them in RANK ORDER.  One
+ * launch per step and rank, S NVLink barriers inside it, bit-identical codebooks on all ranks.
+ * peer_stats[p]: rank p's slot of THIS call (vqb200_rvq_small_stats_floats(S, K) floats, the
+ * same slot index on every rank; alternate two slots between consecutive calls); peer_flags as
+ * for vqb200_ema_finalize_peer; the call consumes the epochs epoch0 .. epoch0 + S - 1;
+ * n_total = vectors of all ranks (perplexity / dcr are global, the loss is this rank's).
+ * Every rank must take this path for the same step: vqb200_rvq_small_peer_eligible(N, D, S, K)
+ * (1 = the whole-GPU variant applies on the current device) must agree across ranks, i.e. shards
+ * of equal size.  world == 1 degenerates to vqb200_rvq_small_forward. */
+int vqb200_rvq_small_peer_eligible(int64_t N, int64_t D, int32_t S, const int64_t* K);
+size_t vqb200_rvq_small_stats_floats(int32_t S, const int64_t* K);
+int vqb200_rvq_small_forward_peer(const float* z, int64_t B, int64_t C, int64_t T,
+                                  int64_t sB, int64_t sC, int64_t sT, int32_t S,
+                                  float* const* E, float* const* ema_cluster_size, float* const* ema_w,
+                                  const int64_t* K, double decay, double eps, float commitment_cost,
+                                  float* workspace, double* sse, int32_t* idx, float* out, float* m3,
+                                  const float* const* peer_stats, uint32_t* const* peer_flags,
+                                  int32_t rank, int32_t world, uint32_t epoch0, int64_t n_total,
+                                  vqb200_stream_t stream);
+
 /* ---- loss + metrics as device scalars ----------------- models/vqvae.py:55-61,66-74 (a7,a9) -
  * out3 = {loss, perplexity, dcr}.  loss = c*mse (EMA) or mse + c*mse (standard), mse = sse/numel;
  * perplexity = exp(-sum p log(p+1e-10)), p = cnt/N; dcr = 1 - #{cnt>0}/K. */
