@@ -63,6 +63,18 @@ for transport in ("nccl", "peer"):
     z = 0.5 * torch.randn(4096 // world, 64, 10, device=dev)
     with torch.no_grad():
         out[f"rvq4 k1024 step, 40960 vectors total, {transport}"] = {"us": timeit(lambda: m(z), reps=50, warm=5)}
+# cfg2-like sharded step: RVQ 4 x K=512 on 512 vectors PER RANK -- multi-kernel path with the peer finalize vs the
+# single-launch kernel with the exchange inside (uniform shards)
+for tag, uniform in (("multi-kernel + peer finalize", False), ("single launch, exchange inside", True)):
+    vqb200.dist.enable(peer="peer", uniform_shards=uniform)
+    torch.manual_seed(4)
+    m = vqb200.ResidualVQ(4, 512, 64, use_ema=True).to(dev).train()
+    with torch.no_grad():
+        for l in m.layers:
+            l.embedding.weight.normal_(0, 0.3); l.ema_w.copy_(l.embedding.weight); l.ema_cluster_size.fill_(1)
+    z = 0.5 * torch.randn(512, 64, 1, device=dev)
+    with torch.no_grad():
+        out[f"rvq4 k512 step, 512 vectors per rank, {tag}"] = {"us": timeit(lambda: m(z), reps=100, warm=10)}
 vqb200.dist.disable()
 if rank == 0:
     print(json.dumps(out))
