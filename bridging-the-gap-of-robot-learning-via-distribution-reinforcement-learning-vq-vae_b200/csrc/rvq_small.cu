@@ -353,18 +353,25 @@ rvq_small_kernel(const Args a) {
 }  // namespace small
 
 // ==========================================================================================
-// Wide variant (the BASELINE cfg2 shape and its neighbours: N <= 1024, S * K <= 3072): the same algorithm spread
-// over the whole GPU instead of one GPC.  Grid = 16 row blocks x 8 code slices = 128 CTAs; the 8 CTAs that share a
-// row block form a cluster.  What makes it fast is the dependency chain, not the FLOPs:
+// Wide variant (the BASELINE cfg2 shape and its neighbours: N <= 64 x row blocks, sum_s ceil(K_s / 8) <= 384): the same
+// algorithm spread over the whole GPU instead of one GPC.  Grid = row blocks x 8 code slices, 512 threads; the 8 CTAs
+// that share a row block form a cluster; the number of row blocks is what cudaOccupancyMaxActiveClusters reports as
+// co-resident (15 on a B200).  What makes it fast is the dependency chain, not the FLOPs:
 //   * every CTA loads its code slice of EVERY stage (pre-update codebooks, known at launch) once, up front;
-//   * per stage: partial argmin over the slice -> ONE cluster barrier, candidates merged through distributed shared
-//     memory (64-bit keys, cand_better order) -> EMA statistics as L2 reductions -> ONE grid barrier -> every CTA
-//     derives cs', n and the updated codewords of its rows' codes locally (same formulas, same bits as the in-place
-//     update) and applies gather / residual / running sum to its private copy of the row block;
-//   * the in-place update of (ema_cluster_size, ema_w, embedding) of stage s is deferred until the next grid barrier
-//     has proven that nobody reads the old values any more.
-// The grid barrier is a monotonically increasing counter in the workspace with a bounded spin (a protocol bug traps
-// instead of hanging the GPU); the launch is cooperative, so all 128 CTAs are co-resident.
+//   * per stage: register-tiled exact distances over the slice (4 rows x 4 codes per lane) -> ONE cluster barrier,
+//     candidates merged through distributed shared memory (64-bit keys, cand_better order) -> EMA statistics as L2
+//     reductions -> ONE grid barrier -> every CTA derives cs', n and the updated codewords of its rows' codes locally
+//     (same formulas, same bits as the in-place update) and applies gather / residual / running sum to its private copy
+//     of the row block;
+//   * the in-place updates of (ema_cluster_size, ema_w, embedding) of ALL stages are deferred past the last grid
+//     barrier (nobody reads the old values any more) and done as one flattened pass; CTA s reports stage s's metrics and
+//     the last reporter adds the aggregate row m3[S];
+//   * data-parallel ranks (world > 1): statistics live in NVLink peer slots, the per-stage grid barrier also spans the
+//     ranks (grid_barrier_world) and every read of [dw | cnt] is a rank-ordered sum over all slots.
+// The grid barrier is a monotonically increasing counter in the workspace with a bounded spin (a protocol bug prints
+// and traps instead of hanging the GPU); the launch is cooperative, so all CTAs are co-resident.  Under Nsight Compute
+// (which cannot launch cooperative + clustered kernels) the attribute is dropped; VQB200_RVQ_STAMPS=1 prints the phase
+// timeline of CTA 0.
 // ==========================================================================================
 namespace wide {
 using small::Args;
