@@ -86,3 +86,29 @@ def test_shard_bounds_cover():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_peer_exchange_slot_and_epoch_bookkeeping():
+    """Host-side protocol of the peer-memory exchange (dist.PeerExchange.next_slot) without a GPU: slots alternate per
+    USE, a use consumes as many barrier epochs as it has stages, epochs never repeat and wrap at 2^32."""
+    import ctypes
+    import vqb200
+    from vqb200.dist import PeerExchange, FLAG_BYTES
+    px = PeerExchange.__new__(PeerExchange)
+    px.epoch, px.uses, px.slot_bytes, px._own = 1, 0, 1024, 1 << 20           # epoch 1 = the handshake
+    px.base = [1 << 20, 2 << 20]
+    px._slots = [(ctypes.c_void_p * 2)(*[b + FLAG_BYTES + s * px.slot_bytes for b in px.base]) for s in range(2)]
+    seen = []
+    e, mine, tab = px.next_slot()             # a finalize call: one epoch
+    seen.append((e, mine)); assert e == 2 and tab[0] == mine
+    e, mine, tab = px.next_slot(4)            # a single-launch ResidualVQ with 4 stages: epochs 3..6
+    seen.append((e, mine)); assert e == 3 and px.epoch == 6
+    e, mine, tab = px.next_slot()
+    seen.append((e, mine)); assert e == 7
+    slots = [m for _, m in seen]
+    assert slots[0] != slots[1] and slots[0] == slots[2]                       # alternate per use, not per epoch
+    assert {m - px._own - FLAG_BYTES for m in slots} == {0, px.slot_bytes}
+    px.epoch = 0xFFFFFFFE
+    e, _, _ = px.next_slot(4)
+    assert e == 0xFFFFFFFF and px.epoch == 2                                    # wraps; kernels compare (int)(seen - epoch) >= 0
+    assert px.fits(3, 64) and not px.fits(4, 64)
