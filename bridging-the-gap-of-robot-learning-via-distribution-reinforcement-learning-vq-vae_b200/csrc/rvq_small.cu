@@ -483,6 +483,70 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define VQ_STAMP(i) do { if (a.stamps && blockIdx.x == 0 && threadIdx.x == 0 && (i) < 64) { stamp[(i)] = gtime(); if ((i) == 0) cyc0 = clock64(); } } while (0)
 
+// One pass of exact distances for this CTA: warp tile = (8 * RI) rows x 16 codes, lane = RI rows x 4 codes (rows
+// i*8 + rg, codes j*4 + cg).  Candidates go to ckey[] with 64-bit atomicMin (cand_better order).
+template <int RI>
+__device__ __forceinline__ void k1_tiles(const float* __restrict__ R, const float* __restrict__ Esl,
+                                         const float* __restrict__ eesl, const float* __restrict__ xxs,
+                                         unsigned long long* __restrict__ ckey, int rows, int ks, int k0s, int warp, int lane) {
+  const int rg = lane >> 2, cg = lane & 3;
+  const int code_blocks = (ks + 15) >> 4;
+  const int tiles = ((rows + 8 * RI - 1) / (8 * RI)) * code_blocks;
+  for (int t = warp; t < tiles; t += NW) {
+    const int rblk = t / code_blocks, cblk = t - rblk * code_blocks;
+    int rI[RI], kI[4];
+#pragma unroll
+    for (int i = 0; i < RI; ++i) rI[i] = rblk * (8 * RI) + i * 8 + rg;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) kI[j] = cblk * 16 + j * 4 + cg;
+    const float4* xp[RI]; const float4* ep[4];
+#pragma unroll
+    for (int i = 0; i < RI; ++i) xp[i] = reinterpret_cast<const float4*>(R + min(rI[i], rows - 1) * LDR);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ep[j] = reinterpret_cast<const float4*>(Esl + min(kI[j], ks - 1) * LDE);
+    float acc[RI][4];
+#pragma unroll
+    for (int i = 0; i < RI; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < D / 4; ++c) {
+      float4 xv[RI], ev[4];
+#pragma unroll
+      for (int i = 0; i < RI; ++i) xv[i] = xp[i][c];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ev[j] = ep[j][c];
+#pragma unroll
+      for (int i = 0; i < RI; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float d = acc[i][j];
+          d = fmaf(xv[i].x, ev[j].x, d); d = fmaf(xv[i].y, ev[j].y, d);
+          d = fmaf(xv[i].z, ev[j].z, d); d = fmaf(xv[i].w, ev[j].w, d);
+          acc[i][j] = d;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < RI; ++i) {
+      unsigned long long best = ~0ull;
+      const float xx = xxs[min(rI[i], rows - 1)];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (kI[j] < ks) {
+          const float dd = __fsub_rn(__fadd_rn(xx, eesl[kI[j]]), __fmul_rn(2.0f, acc[i][j]));
+          const unsigned long long key = cand_key(dd, k0s + kI[j]);
+          best = key < best ? key : best;
+        }
+      }
+      unsigned long long o = __shfl_xor_sync(0xffffffffu, best, 1);
+      best = o < best ? o : best;
+      o = __shfl_xor_sync(0xffffffffu, best, 2);
+      best = o < best ? o : best;
+      if (cg == 0 && rI[i] < rows) atomicMin(ckey + rI[i], best);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NT, 1)
 rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
   __shared__ unsigned long long stamp[64];
@@ -619,58 +683,12 @@ rvq_wide_kernel(const Args a, unsigned* __restrict__ barrier) {
       }
       __syncthreads();
       if (s == 0) VQ_STAMP(40);
-      const int rg = lane >> 2, cg = lane & 3;
-      const int code_blocks = (ks + 15) >> 4;
-      const int tiles = ((rows + 31) >> 5) * code_blocks;
-      for (int t = warp; t < tiles; t += NW) {
-        const int rblk = t / code_blocks, cblk = t - rblk * code_blocks;
-        int rI[4], kI[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { rI[i] = rblk * 32 + i * 8 + rg; kI[i] = cblk * 16 + i * 4 + cg; }
-        const float4* xp[4]; const float4* ep[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          xp[i] = reinterpret_cast<const float4*>(R + min(rI[i], rows - 1) * LDR);
-          ep[i] = reinterpret_cast<const float4*>(Esl + min(kI[i], ks - 1) * LDE);
-        }
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
-        for (int c = 0; c < D / 4; ++c) {
-          float4 xv[4], ev[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { xv[i] = xp[i][c]; ev[i] = ep[i][c]; }
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float d = acc[i][j];
-              d = fmaf(xv[i].x, ev[j].x, d); d = fmaf(xv[i].y, ev[j].y, d);
-              d = fmaf(xv[i].z, ev[j].z, d); d = fmaf(xv[i].w, ev[j].w, d);
-              acc[i][j] = d;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          unsigned long long best = ~0ull;
-          const float xx = xxs[min(rI[i], rows - 1)];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (kI[j] < ks) {
-              const float dd = __fsub_rn(__fadd_rn(xx, eesl[kI[j]]), __fmul_rn(2.0f, acc[i][j]));
-              const unsigned long long key = cand_key(dd, k0s + kI[j]);
-              best = key < best ? key : best;
-            }
-          }
-          unsigned long long o = __shfl_xor_sync(0xffffffffu, best, 1);
-          best = o < best ? o : best;
-          o = __shfl_xor_sync(0xffffffffu, best, 2);
-          best = o < best ? o : best;
-          if (cg == 0 && rI[i] < rows) atomicMin(ckey + rI[i], best);
-        }
+      // rows per lane: the smallest register tile that still gives every tile to a warp in one pass (more warps busy,
+      // fewer padded rows); larger slices fall back to the 4 x 4 tile with the best FMA : shared-load ratio
+      {
+        const int code_blocks = (ks + 15) >> 4;
+        if (((rows + 15) >> 4) * code_blocks <= NW) k1_tiles<2>(R, Esl, eesl, xxs, ckey, rows, ks, k0s, warp, lane);
+        else k1_tiles<4>(R, Esl, eesl, xxs, ckey, rows, ks, k0s, warp, lane);
       }
       if (s == 0) VQ_STAMP(41);
     }
