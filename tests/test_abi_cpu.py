@@ -50,6 +50,30 @@ def test_argument_errors_do_not_need_a_gpu():
     assert rc == -1 and "null" in vqb200._lib.last_error()
     rc = lib.vqb200_fsq_forward(None, 1, 99, 1, None, 1000, None, None, None, None, None)
     assert rc < 0
+    # peer-memory exchange (csrc/peer.cu): argument checks come before any CUDA call
+    import ctypes
+    dummy = (ctypes.c_void_p * 2)(0x1000, 0x2000)
+    assert lib.vqb200_peer_barrier(dummy, 0, 17, ctypes.c_uint32(1), None) == -2          # > VQB200_MAX_PEERS ranks
+    assert lib.vqb200_peer_barrier(dummy, 2, 2, ctypes.c_uint32(1), None) == -2           # rank outside the world
+    assert lib.vqb200_peer_barrier(None, 0, 1, ctypes.c_uint32(1), None) == -1
+    assert lib.vqb200_peer_open(None, None) == -1 and lib.vqb200_peer_alloc(0, None, None) == -1
+    assert lib.vqb200_ema_finalize_peer(dummy, dummy, 0, 2, ctypes.c_uint32(1), None, None, None, None, 8, 8,
+                                        0.99, 1e-5, None, None, None, None, None) == -1
+    assert lib.vqb200_peer_close(None) == 0 and lib.vqb200_peer_free(None) == 0           # NULL is a no-op
+
+
+def test_single_launch_rvq_size_queries_need_no_gpu():
+    import ctypes
+    import vqb200
+    lib = vqb200._lib.load()
+    K = (ctypes.c_int64 * 4)(512, 512, 512, 512)
+    assert lib.vqb200_rvq_small_eligible(512, 64, 4, K) == 1
+    assert lib.vqb200_rvq_small_eligible(512, 32, 4, K) == 0 and lib.vqb200_rvq_small_eligible(5000, 64, 4, K) == 0
+    # per stage [dw (K*64) | cnt (K)] padded to 16 bytes; the workspace adds K + 8 scratch floats per stage + 16
+    assert lib.vqb200_rvq_small_stats_floats(4, K) == 4 * 512 * 65
+    assert lib.vqb200_rvq_small_workspace_floats(4, K) == 4 * 512 * 65 + 4 * (512 + 8) + 16
+    K_odd = (ctypes.c_int64 * 2)(333, 7)
+    assert lib.vqb200_rvq_small_stats_floats(2, K_odd) == (333 * 65 + 3) // 4 * 4 + (7 * 65 + 3) // 4 * 4
 
 
 def test_state_dict_keys_match_reference():
