@@ -14,7 +14,7 @@ from . import build as _build
 _P = c_void_p
 _LIB = None
 
-ASSIGN_AUTO, ASSIGN_SIMT, ASSIGN_TC = 0, 1, 2
+ASSIGN_AUTO, ASSIGN_SIMT, ASSIGN_TC, ASSIGN_TC_SPLIT = 0, 1, 2, 3
 
 _SIGNATURES = {
     # name: (restype, [argtypes])

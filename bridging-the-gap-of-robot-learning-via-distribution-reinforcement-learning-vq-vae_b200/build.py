@@ -8,9 +8,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libvqb200.so")
-SOURCES = ["abi.cu", "assign.cu", "assign_simt.cu", "assign_tc.cu", "assign_tc_gen.cu", "ema.cu", "peer.cu", "gather.cu", "tile_ops.cu", "rvq_small.cu", "fsq_lfq.cu", "fsq_lfq_fused.cu", "tokens.cu"]
+SOURCES = ["abi.cu", "assign.cu", "assign_simt.cu", "assign_tc.cu", "assign_f16.cu", "assign_tc_gen.cu", "ema.cu", "peer.cu", "gather.cu", "tile_ops.cu", "rvq_small.cu", "fsq_lfq.cu", "fsq_lfq_fused.cu", "tokens.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O2", "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC,-O2"]
 
 
 def _nvcc():
@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
     obj_dir = os.path.join(HERE, "build")
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = list(NVCC_FLAGS)
     flags += os.environ.get("VQB200_NVCC_EXTRA", "").split()          # development: e.g. -DVQB200_TOP2_VARIANT=0
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     procs = []

@@ -19,6 +19,13 @@ int launch_assign_tc_gen(const ZView& z, const float* E, const float* ee, const 
                          int K, int D, int32_t* idx, float* best, void* workspace, size_t workspace_bytes,
                          cudaStream_t stream);
 size_t assign_tc_gen_workspace_bytes(long long N, int D);
+bool assign_f16_eligible(const ZView& z, int K, int D);
+int launch_assign_f16(const ZView& z, const float* E, const float* ee, const void* image, const float* info,
+                      int K, int D, int32_t* idx, float* best, void* workspace, size_t workspace_bytes,
+                      cudaStream_t stream, const int32_t* prev_idx = nullptr, const float* prev_E = nullptr,
+                      int prev_K = 0, float* r_out = nullptr);
+bool assign_f16_can_fuse_residual(const ZView& z, const float* r_out);
+size_t assign_f16_workspace_bytes(long long N);
 }  // namespace vqb200
 
 using namespace vqb200;
@@ -27,7 +34,8 @@ extern "C" {
 
 size_t vqb200_assign_workspace_bytes(int64_t N, int64_t D) {
   if (D == 128 || D == 256 || D == 512) return assign_tc_gen_workspace_bytes(N, (int)D);
-  return assign_tc_workspace_bytes(N);
+  const size_t a = assign_tc_workspace_bytes(N), b = assign_f16_workspace_bytes(N);
+  return a > b ? a : b;
 }
 
 int vqb200_vq_assign(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,
@@ -46,6 +54,8 @@ int vqb200_vq_assign(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB
   const bool gen = assign_tc_gen_eligible(zv, (int)K, D);          // D = 128 / 256: bf16 row-image variant
   const bool eligible = gen || assign_tc_eligible(zv, (int)K, D);  // D = 64: in-place conversion variant
   const size_t need = vqb200_assign_workspace_bytes(zv.N, D);
+  const bool split = (algo == VQB200_ASSIGN_TC_SPLIT);        // development: the round-1 split-bf16 kernel (D == 64)
+  if (split) algo = VQB200_ASSIGN_TC;
   if (algo == VQB200_ASSIGN_TC) {
     VQ_CHECK_ARG(image && info && workspace, VQB200_EINVAL, "vq_assign(TC): image, info and workspace are required");
     VQ_CHECK_ARG(!best, VQB200_EUNSUPPORTED, "vq_assign(TC): the winning distance is only produced by the SIMT algorithm");
@@ -57,7 +67,8 @@ int vqb200_vq_assign(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB
     VQ_CHECK_ARG(algo == VQB200_ASSIGN_SIMT, VQB200_EINVAL, "vq_assign: unknown algo %d", algo);
   }
   if (use_tc && gen) return launch_assign_tc_gen(zv, E, ee, image, info, (int)K, D, idx, best, workspace, workspace_bytes, stream);
-  if (use_tc) return launch_assign_tc(zv, E, ee, image, info, (int)K, D, idx, best, workspace, workspace_bytes, stream);
+  if (use_tc && split) return launch_assign_tc(zv, E, ee, image, info, (int)K, D, idx, best, workspace, workspace_bytes, stream);
+  if (use_tc) return launch_assign_f16(zv, E, ee, image, info, (int)K, D, idx, best, workspace, workspace_bytes, stream);
   return launch_assign_simt(zv, E, ee, (int)K, D, idx, best, nullptr, nullptr, zv.N, stream);
 }
 
@@ -82,11 +93,16 @@ int vqb200_vq_assign_residual(const float* r_in, int64_t B, int64_t C, int64_t T
   if (B * T == 0) return VQB200_OK;
   const ZView zv = make_zview(r_in, B, C, T, sB, sC, sT);
   const int D = (int)C;
+  const bool split = (algo == VQB200_ASSIGN_TC_SPLIT);
+  if (split) algo = VQB200_ASSIGN_TC;
   const bool tc_ok = (algo == VQB200_ASSIGN_AUTO || algo == VQB200_ASSIGN_TC) && image && info && workspace &&
-                     assign_tc_eligible(zv, (int)K, D) && workspace_bytes >= assign_tc_workspace_bytes(zv.N) &&
-                     (zv.N >= 2048 || algo == VQB200_ASSIGN_TC) && assign_tc_can_fuse_residual(zv, r_out);
-  if (tc_ok)
+                     assign_f16_eligible(zv, (int)K, D) && workspace_bytes >= vqb200_assign_workspace_bytes(zv.N, D) &&
+                     (zv.N >= 2048 || algo == VQB200_ASSIGN_TC) && assign_f16_can_fuse_residual(zv, r_out);
+  if (tc_ok && split)
     return launch_assign_tc(zv, E, ee, image, info, (int)K, D, idx, nullptr, workspace, workspace_bytes, stream,
+                            idx_prev, E_prev, (int)K_prev, r_out);
+  if (tc_ok)
+    return launch_assign_f16(zv, E, ee, image, info, (int)K, D, idx, nullptr, workspace, workspace_bytes, stream,
                             idx_prev, E_prev, (int)K_prev, r_out);
   const int rc = vqb200_vq_gather_st(r_in, B, C, T, sB, sC, sT, E_prev, idx_prev, K_prev, nullptr, r_out, nullptr, 0,
                                      nullptr, stream_);

@@ -1,6 +1,7 @@
 // vqb200 K3: EMA statistics (scatter-add) + EMA finalize, codebook-derived state, histogram,
 // standard-VQ codebook gradient.  Replaces models/vqvae.py:44-50 and :35 of the reference.
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include "codebook.cuh"
 
 namespace vqb200 {
@@ -155,7 +156,7 @@ ema_finalize_cs_kernel(const float* __restrict__ cnt, float* __restrict__ cs, in
   }
   if (threadIdx.x == 0) {
     scratch[K] = n;
-    if (info) { info[0] = 0.f; info[1] = 0.f; info[2] = 0.f; info[3] = 0.f; }
+    if (info) { info[0] = 0.f; info[1] = 0.f; info[2] = INFO2_RESET; info[3] = 0.f; }
   }
 }
 
@@ -203,7 +204,94 @@ backward_codebook_kernel(const float* __restrict__ dw1, long long n, const float
     gE[i] = s * dw1[i];
 }
 
-__global__ void info_reset_kernel(float* info) { if (threadIdx.x < 4) info[threadIdx.x] = 0.f; }
+__global__ void info_reset_kernel(float* info) { if (threadIdx.x < 4) info[threadIdx.x] = (threadIdx.x == 2) ? INFO2_RESET : 0.f; }
+
+// ------------------------------------------------------------------------------------------
+// fp16 filter image (codebook.cuh): one CTA per 128-code tile.  Runs after E / ee have been refreshed.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+codebook_image_f16_kernel(const float* __restrict__ E, int K, unsigned char* __restrict__ image, float* __restrict__ info) {
+  constexpr int D = IMG_TILE_DIMS;
+  __shared__ float s_red[8];
+  __shared__ float s_scale;
+  const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k0 = j * IMG_TILE_CODES;
+  // 128 codes x 16 float4: thread t owns float4 q = t & 15 of rows (t >> 4) + 16 i
+  float4 v[8];
+  float m = 0.f;
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = (tid >> 4) + 16 * i, k = k0 + r;
+    v[i] = (k < K) ? __ldg(reinterpret_cast<const float4*>(E + (size_t)k * D) + (tid & 15)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float a = fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w)));
+    bad |= !(a <= 3.0e38f);
+    m = fmaxf(m, a);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) s_red[warp] = m;
+  __syncthreads();
+  if (tid == 0) {
+    float mm = 0.f;
+    for (int w = 0; w < 8; ++w) mm = fmaxf(mm, s_red[w]);
+    // s_j = 2^(10 - floor(log2 mm)); tiles whose maximum is below 2^-100 (or not finite) cannot be represented
+    const int eb = (int)((__float_as_uint(mm) >> 23) & 255u);
+    float scale = 1.0f, inv = 1.0f;
+    if (mm != 0.f) {
+      if (eb < 27 || eb == 255) { bad = true; }
+      else { scale = __uint_as_float((unsigned)(264 - eb) << 23); inv = __uint_as_float((unsigned)(eb - 10) << 23); }
+    }
+    s_scale = scale;
+    float* meta = reinterpret_cast<float*>(image + img_f16_meta_offset(K, D)) + (size_t)j * F16_META_FLOATS;
+    meta[IMG_TILE_CODES + 0] = inv; meta[IMG_TILE_CODES + 1] = 0.f; meta[IMG_TILE_CODES + 2] = 0.f; meta[IMG_TILE_CODES + 3] = 0.f;
+  }
+  bad = __syncthreads_or(bad);
+  const float sc = s_scale;
+  unsigned char* tile = image + img_f16_offset(K, D) + (size_t)j * F16_TILE_BYTES;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = (tid >> 4) + 16 * i, q = tid & 15;      // float4 q covers dims 4q..4q+3: half of 16-byte chunk q >> 1
+    const __half2 h0 = __floats2half2_rn(v[i].x * sc, v[i].y * sc);
+    const __half2 h1 = __floats2half2_rn(v[i].z * sc, v[i].w * sc);
+    uint2 w;
+    w.x = *reinterpret_cast<const unsigned*>(&h0);
+    w.y = *reinterpret_cast<const unsigned*>(&h1);
+    *reinterpret_cast<uint2*>(tile + r * 128 + (((q >> 1) ^ (r & 7)) << 4) + (q & 1) * 8) = w;
+  }
+  {
+    // interleaved fp32 copy for the exact re-rank: thread (r = tid >> 4, q = tid & 15) holds dims 4q..4q+3 of rows r + 16 i
+    float4* e4 = reinterpret_cast<float4*>(image + img_e4_offset(K, D)) + (size_t)j * (IMG_TILE_CODES * 16);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = (tid >> 4) + 16 * i, q = tid & 15;
+      e4[(size_t)(r >> 2) * 64 + q * 4 + (r & 3)] = v[i];
+    }
+  }
+  float nmin = INFO2_RESET;
+  if (tid < IMG_TILE_CODES) {
+    const int k = k0 + tid;
+    float* meta = reinterpret_cast<float*>(image + img_f16_meta_offset(K, D)) + (size_t)j * F16_META_FLOATS;
+    // -|E_k|^2/2 as the finalize / prepare kernel has just written it behind the split tiles (-inf for padding codes)
+    const float nh = reinterpret_cast<const float*>(image + img_tiles_bytes(K, D))[k];
+    // padding codes: a large FINITE negative (the filter packs a group id into the low mantissa bits of its scores,
+    // which would turn -inf into a NaN)
+    meta[tid] = (k < K) ? nh : -3.0e38f;
+    if (k < K && nh == nh) nmin = sqrtf(-2.0f * nh);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nmin = fminf(nmin, __shfl_xor_sync(0xffffffffu, nmin, o));
+  if (info && lane == 0 && warp < 4) atomicMin(reinterpret_cast<int*>(info + 2), __float_as_int(nmin));
+  if (info && tid == 0 && bad) atomicExch(reinterpret_cast<int*>(info + 1), __float_as_int(1.0f));
+}
+
+int launch_image_f16(const float* E, long long K, long long D, void* image, float* info, cudaStream_t stream) {
+  if (!image || !img_has_f16(D)) return VQB200_OK;
+  VQ_CHECK_ARG((reinterpret_cast<uintptr_t>(E) & 15) == 0, VQB200_EALIGN, "codebook image: E must be 16-byte aligned");
+  codebook_image_f16_kernel<<<(int)(img_kp(K) / IMG_TILE_CODES), 256, 0, stream>>>(E, (int)K, (unsigned char*)image, info);
+  VQ_LAUNCH_CHECK("codebook_image_f16_kernel");
+  return VQB200_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 // Codebook health (opt-in, NOT in the reference): codes whose usage fell below a threshold are
@@ -260,7 +348,7 @@ int vqb200_codebook_prepare(const float* E, int64_t K, int64_t D, float* ee, voi
   const int grid = grid_for(Kp, 8, sm_count() * 8);
   codebook_prepare_kernel<<<grid, 256, 0, stream>>>(E, (int)K, (int)D, ee, (unsigned char*)image, info);
   VQ_LAUNCH_CHECK("codebook_prepare_kernel");
-  return VQB200_OK;
+  return launch_image_f16(E, K, D, image, info, stream);
 }
 
 int vqb200_ema_accumulate(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,
@@ -313,7 +401,7 @@ int vqb200_ema_finalize(const float* stats, float* ema_cluster_size, float* ema_
   ema_finalize_w_kernel<<<grid, 256, 0, stream>>>(dw, ema_w, E, (int)K, (int)D, fd, fo, scratch, ee,
                                                   (unsigned char*)image, info);
   VQ_LAUNCH_CHECK("ema_finalize_w_kernel");
-  return VQB200_OK;
+  return launch_image_f16(E, K, D, image, info, stream);
 }
 
 int vqb200_codebook_revive(const float* z, int64_t B, int64_t C, int64_t T, int64_t sB, int64_t sC, int64_t sT,

@@ -93,7 +93,7 @@ finalize_cs_kernel(const Table t, float* __restrict__ cnt_out, float* __restrict
     scratch[k] = __fmul_rn(__fdiv_rn(__fadd_rn(cs[k], eps), __fadd_rn(n, k_eps)), n);
   if (threadIdx.x == 0) {
     scratch[K] = n;
-    if (info) { info[0] = 0.f; info[1] = 0.f; info[2] = 0.f; info[3] = 0.f; }
+    if (info) { info[0] = 0.f; info[1] = 0.f; info[2] = INFO2_RESET; info[3] = 0.f; }
   }
 }
 
@@ -237,7 +237,7 @@ int vqb200_ema_finalize_peer(const float* const* peer_stats, uint32_t* const* pe
   peer::finalize_w_kernel<<<grid, 256, 0, stream>>>(t, ema_w, E, (int)K, (int)D, fd, fo, scratch, ee,
                                                     (unsigned char*)image, info);
   VQ_LAUNCH_CHECK("peer::finalize_w_kernel");
-  return VQB200_OK;
+  return launch_image_f16(E, K, D, image, info, stream);
 }
 
 }  // extern "C"

@@ -6,7 +6,7 @@
 namespace vqb200 {
 namespace ptx {
 
-constexpr unsigned SPIN_LIMIT = 1u << 22;   // bounded waits: a protocol bug traps instead of hanging the GPU
+constexpr unsigned SPIN_LIMIT = 1u << 20;   // bounded waits: a protocol bug traps instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -19,9 +19,22 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" :: "r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint, in ns,
+// expires) instead of returning at once -- a plain spin loop of waiting warps was measured to burn 38 % of the SM's
+// issue slots in the assignment kernel (BRA / ISETP / IADD3 / SYNCS / YIELD in the ncu source page)
+#ifndef VQB200_MBAR_HINT_NS
+#define VQB200_MBAR_HINT_NS 20000
+#endif
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)VQB200_MBAR_HINT_NS) : "memory");
+  return ok != 0;
+}
+// non-blocking probe (mbarrier.test_wait never suspends the thread)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
                : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }

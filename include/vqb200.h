@@ -45,6 +45,7 @@ typedef void* vqb200_stream_t;   /* cudaStream_t */
 #define VQB200_ASSIGN_AUTO  0    /* tcgen05 filter + exact rerank when eligible, else SIMT  */
 #define VQB200_ASSIGN_SIMT  1    /* exact fp32 CUDA-core path                               */
 #define VQB200_ASSIGN_TC    2    /* force the tcgen05 path (error if not eligible)          */
+#define VQB200_ASSIGN_TC_SPLIT 3 /* development: round-1 three-pass split-bf16 kernel (D = 64) */
 
 int         vqb200_abi_version(void);
 const char* vqb200_last_error_string(void);

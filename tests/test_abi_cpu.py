@@ -35,9 +35,13 @@ def test_library_exports_every_declared_symbol():
 def test_size_queries_need_no_gpu():
     import vqb200
     lib = vqb200._lib.load()
-    # 1024 x 64 split-bf16 image = 8 code tiles x (16 KiB hi + 16 KiB lo) + 1024 fp32 values of -|E|^2/2
-    assert lib.vqb200_codebook_image_bytes(1024, 64) == 8 * 32768 + 1024 * 4
-    assert lib.vqb200_codebook_image_bytes(1000, 24) == 8 * 32768 + 1024 * 4
+    # split-bf16 image = 8 code tiles x (16 KiB hi + 16 KiB lo) + 1024 fp32 values of -|E|^2/2
+    split = 8 * 32768 + 1024 * 4
+    assert lib.vqb200_codebook_image_bytes(1000, 24) == split
+    # D == 64 appends (1 KiB aligned) the fp16 filter image: 8 x 16 KiB tiles + 8 x 528 B meta records, and (1 KiB
+    # aligned) the group-interleaved fp32 copy for the exact re-rank
+    f16 = -(-split // 1024) * 1024 + 8 * 16384 + 8 * 528
+    assert lib.vqb200_codebook_image_bytes(1024, 64) == -(-f16 // 1024) * 1024 + 1024 * 64 * 4
     assert lib.vqb200_unique_workspace_bytes() > 256 * 1024
     assert lib.vqb200_assign_workspace_bytes(1000, 64) >= 1000 * 4
     assert lib.vqb200_assign_workspace_bytes(1000, 256) >= 1024 * 256 * 4   # + split-bf16 row image

@@ -32,6 +32,10 @@ def case(B, T, K, regime="small", seed=0, time_it=False, perm=False, D=64):
         W[: K // 2] *= 1e5
     elif regime == "dup":
         W[K // 2:] = W[: K - K // 2]
+    elif regime == "dead":               # a few live codes among huge dead ones (the reference after its first EMA steps)
+        W[::3] *= 3e4
+    elif regime == "tiny":
+        W *= 1e-4
     st = vqb200.QuantizerState(K, D, dev)
     if perm:
         z = (0.5 * torch.randn(B, T, D, device=dev)).permute(0, 2, 1)
@@ -42,9 +46,10 @@ def case(B, T, K, regime="small", seed=0, time_it=False, perm=False, D=64):
     torch.cuda.synchronize()
     off = (-st._assign_ws.data_ptr()) % 1024 if D != 64 else 0
     ws = st._assign_ws[off:off + 256].view(torch.int32)
-    flagged, err = int(ws[0]), int(ws[1])
+    flagged, err, two, wide, rr = int(ws[0]), int(ws[1]), int(ws[2]) + int(ws[3]), int(ws[4]), int(ws[5])
     mism = int((i_simt != i_tc).sum())
-    out = dict(B=B, T=T, K=K, D=D, regime=regime, perm=perm, N=B * T, mismatches=mism, flagged=flagged, err=err)
+    out = dict(B=B, T=T, K=K, D=D, regime=regime, perm=perm, N=B * T, mismatches=mism, flagged=flagged,
+               multi_groups=two, wide=wide, rerank_list=rr, err=err)
     if mism:
         bad = (i_simt != i_tc).reshape(-1).nonzero().reshape(-1)[:5]
         out["first_bad_rows"] = bad.tolist()
@@ -52,6 +57,8 @@ def case(B, T, K, regime="small", seed=0, time_it=False, perm=False, D=64):
         out["tc"] = i_tc.reshape(-1)[bad].tolist()
     if time_it:
         out["ms_tc"] = timeit(lambda: vqb200.vq_assign(z, W, st, _lib.ASSIGN_TC))
+        if D == 64:
+            out["ms_tc_split"] = timeit(lambda: vqb200.vq_assign(z, W, st, _lib.ASSIGN_TC_SPLIT))
         out["ms_simt"] = timeit(lambda: vqb200.vq_assign(z, W, st, _lib.ASSIGN_SIMT), reps=2, warm=1)
         fl = 2.0 * B * T * K * D
         out["tc_TFLOPs"] = fl / (out["ms_tc"] * 1e-3) / 1e12
@@ -68,6 +75,14 @@ if __name__ == "__main__":
     total += case(4096, 10, 1000, "normal")
     total += case(512, 1, 512, "init", perm=True)
     total += case(3686, 10, 1024, "degenerate")
+    total += case(3686, 10, 1024, "dead")
+    total += case(3686, 10, 1024, "tiny")
+    total += case(3686, 10, 1023, "small")
+    total += case(3686, 10, 5, "small")
+    total += case(4096, 10, 512, "init")
+    total += case(4096, 10, 256, "small")
+    total += case(4096, 10, 128, "normal")
+    total += case(50000, 1, 2048, "small", perm=True)
     total += case(3000, 7, 300, "dup")
     total += case(100000, 10, 1024, time_it=True)
     total += case(1000000, 10, 1024, time_it=True)
