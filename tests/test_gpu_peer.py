@@ -33,7 +33,7 @@ def _finalize_args(lib, st, cs, w, E, K, D, stream):
 
 def _state(lib, K, D, dev):
     nbytes = int(lib.vqb200_codebook_image_bytes(K, D))
-    raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+    raw = torch.zeros(nbytes + 1024, dtype=torch.uint8, device=dev)     # zeros: the image has alignment gaps nobody writes
     off = (-raw.data_ptr()) % 1024
     return {"ee": torch.empty(K, device=dev), "image": raw[off:off + nbytes], "raw": raw,
             "info": torch.zeros(4, device=dev), "scratch": torch.empty(K + 8, device=dev)}
