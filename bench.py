@@ -5,17 +5,23 @@
 
 Headline workload (BASELINE.json configs[2], the config the "1/2/4/8 B200" metric is quoted on):
   ResidualVQ, S=4 stages, K=1024 codes, D=64, training mode (forward + EMA update + backward) on
-  synthetic latents z ~ 0.5*N(0,1) of shape [1 000 000, 64, 10] PER GPU (N = 10 M vectors / GPU, weak
-  scaling: batch sharded on dim 0, the per-stage EMA statistics all-reduced with NCCL over NVLink).
+  synthetic latents z ~ 0.5*N(0,1): 1 000 000 windows x 10 frames = 10 M vectors IN TOTAL, sharded on dim 0 over
+  the N GPUs (strong scaling, the reference's own split of a fixed batch, scripts/train_ablation.py:189,319-328);
+  the per-stage EMA statistics are exchanged over NVLink.  `--scaling weak` keeps 1 M windows PER GPU instead (a short
+  weak-scaling measurement is also reported under other_workloads at N > 1).
 One "step" = one full pass (fwd + EMA + bwd) over the batch.  One JSON line is printed by rank 0.
+`verify` (N > 1, outside the timed region): codebook state bit-identical on all ranks + a sharded 2-step run compared
+with the single-process full-batch run of the same small problem.
 
 `value`     : whole-job vectors/s with inputs resident in HBM (CUDA events, max over ranks).
 `e2e`       : same metric through the public nn.Module call with the step's input copied from pinned HOST
               memory and the result (loss, perplexity, int32 indices) read back to the host every step.
 `roofline`  : dominant kernel (K1 fused distance+argmin) timed alone with CUDA events; algorithmic flops
               2*N*K*D per launch against the measured bf16 tensor peak (MEASURED_PEAKS.json).
-`cpu_baseline`: the numpy oracle port of the reference algorithm on this box's host cores, on a bounded
-              sample of the same workload.  `--impl reference` prints that arm as its own line.
+`cpu_baseline`: the UNMODIFIED reference modules (oracle/_ref/models/vqvae.py, staged by build()) on this box's host
+              cores with torch CPU, on a bounded sample of the same workload (kind "reference"; falls back to the
+              numpy oracle port, kind "port", when the staged copy is missing).  `--impl reference` prints that arm
+              as its own line.
 """
 import argparse
 import json
@@ -38,6 +44,14 @@ WORKLOADS = {
     "cfg1_ema_k1024_d64": dict(kind="vq", S=1, K=1024, D=64, B=4096, T=10),
 }
 HEADLINE = "cfg3_rvq4_k1024_d64"
+
+
+def workload_text(name, cfg, B_total, world):
+    K, D, S, T = cfg["K"], cfg["D"], cfg["S"], cfg["T"]
+    if cfg["kind"] == "rvq":
+        return (f"{name}: ResidualVQ S={S} K={K} D={D} EMA training step (fwd+EMA+bwd), z [{B_total},{D},{T}] fp32 = "
+                f"{B_total * T} vectors in total, sharded on dim 0 over {world} GPU(s), per-stage EMA stats summed across ranks")
+    return f"{name}: VectorQuantizer K={K} D={D} EMA training step (fwd+EMA+bwd), z [{B_total},{D},{T}] fp32 in total"
 
 
 def load_peaks():
@@ -107,12 +121,75 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU arm: numpy oracle port of the reference algorithm
+# CPU arm: the unmodified reference modules (torch CPU), or the numpy oracle port when they are not staged
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_arm(cfg, steps, warmup, sample_windows=None):
-    """Times forward + EMA update + backward of the reference algorithm (oracle port, numpy/OpenBLAS on all
-    host cores) on a bounded sample of the workload.  The reference materialises N x K fp32 matrices, so the
-    sample is a chunk that fits."""
+def cpu_reference_arm(cfg, steps, warmup, chunk_vectors=65536):
+    """Times forward + EMA update + backward of the reference quantizer on all host cores on a bounded sample of the
+    workload.  The reference materialises N x K fp32 matrices, so the sample is a chunk that fits (BASELINE.md §3:
+    65 536 vectors; halved until one step takes < 8 s)."""
+    try:
+        from oracle.stage_ref import load_reference_vqvae
+        ref = load_reference_vqvae()
+    except Exception:
+        return cpu_port_arm(cfg, steps, warmup)
+    import torch
+    K, D, S, T = cfg["K"], cfg["D"], cfg["S"], cfg["T"]
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(cores)           # torchrun exports OMP_NUM_THREADS=1; the reference arm gets every host core
+    torch.manual_seed(1237)
+    if cfg["kind"] == "rvq":
+        mod = ref.ResidualVQ(S, K, D, use_ema=True)
+        layers = list(mod.layers)
+    else:
+        mod = ref.VectorQuantizer(K, D, use_ema=True)
+        layers = [mod]
+    with torch.no_grad():
+        for l in layers:
+            l.embedding.weight.normal_(0, 0.25)
+            l.ema_w.copy_(l.embedding.weight)
+            l.ema_cluster_size.fill_(1.0)
+    mod.train()
+    chunk = chunk_vectors
+    while True:
+        Bs = max(1, min(cfg["B"], chunk // T))
+        z = (0.5 * torch.randn(Bs, D, T)).requires_grad_(True)
+        g = torch.randn(Bs, D, T)
+        one = torch.ones(())
+
+        def step():
+            z.grad = None
+            loss, q, _ = mod(z)
+            torch.autograd.backward([q, loss], [g, one])
+
+        t0 = time.perf_counter()
+        step()
+        probe = time.perf_counter() - t0
+        if probe < 8.0 or chunk <= 8192:
+            break
+        chunk //= 2
+    for _ in range(max(0, min(warmup, 2) - 1)):
+        step()
+    times = []
+    for _ in range(max(1, steps)):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    n = Bs * T
+    return dict(value=n / med, unit=UNIT, cores=cores, kind="reference",
+                sample=f"{Bs} windows x T={T} = {n} vectors per step (chunk of the workload; the reference materialises "
+                       f"N x K), median of {len(times)} steps, unmodified reference modules (models/vqvae.py) on torch "
+                       f"{torch.__version__} CPU, {cores} threads",
+                ms_per_step=med * 1e3)
+
+
+def cpu_port_arm(cfg, steps, warmup, sample_windows=None):
+    """Fallback when oracle/_ref is not staged: the numpy oracle port (numpy/OpenBLAS on all host cores)."""
     import numpy as np
     from oracle import VQState, rvq_forward, rvq_backward
     K, D, S, T = cfg["K"], cfg["D"], cfg["S"], cfg["T"]
@@ -129,7 +206,6 @@ def cpu_reference_arm(cfg, steps, warmup, sample_windows=None):
         fw = rvq_forward(z, stages, True)
         rvq_backward(fw, stages, g, 1.0)
 
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host core
     try:
         from threadpoolctl import threadpool_limits
         limiter = threadpool_limits(limits=os.cpu_count())
@@ -138,7 +214,7 @@ def cpu_reference_arm(cfg, steps, warmup, sample_windows=None):
     for _ in range(max(1, min(warmup, 2))):
         step()
     times = []
-    for _ in range(steps):
+    for _ in range(max(1, steps)):
         t0 = time.perf_counter()
         step()
         times.append(time.perf_counter() - t0)
@@ -149,7 +225,7 @@ def cpu_reference_arm(cfg, steps, warmup, sample_windows=None):
     n = Bs * T
     return dict(value=n / med, unit=UNIT, cores=os.cpu_count(), kind="port",
                 sample=f"{Bs} windows x T={T} = {n} vectors per step (chunk of the workload; the reference "
-                       f"materialises N x K), median of {steps} steps, numpy/OpenBLAS fp32",
+                       f"materialises N x K), median of {steps} steps, numpy/OpenBLAS fp32 (oracle/_ref not staged)",
                 ms_per_step=med * 1e3)
 
 
@@ -173,6 +249,78 @@ def build_module(vqb200, torch, cfg, dev, seed=42):
     return mod.to(dev).train(), layers
 
 
+def bind_to_gpu_numa(torch, local):
+    """Pin this process (and therefore its pinned-memory allocations, first touch) to the NUMA node of its GPU:
+    with every rank on node 0 the end-to-end arm is bound by one socket's memory -> PCIe path.  Best effort."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        devid = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa node unknown"
+        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        allowed = ids & set(os.sched_getaffinity(0)) or ids
+        os.sched_setaffinity(0, allowed)
+        return f"node {node} ({len(allowed)} cpus)"
+    except Exception as ex:  # pragma: no cover
+        return f"not bound ({type(ex).__name__})"
+
+
+def state_checksum(torch, layers):
+    """Bit-level checksum (sum of the int32 views) of every stage's embedding.weight / ema_w / ema_cluster_size."""
+    vals = []
+    for l in layers:
+        for t in (l.embedding.weight.detach(), l.ema_w, l.ema_cluster_size):
+            vals.append(t.contiguous().view(torch.int32).to(torch.int64).sum())
+    return torch.stack(vals)
+
+
+def verify_multi_gpu(torch, vqb200, dist, dev, rank, world, layers, exchange):
+    """Correctness bits for the multi-GPU line (outside the timed region):
+    (1) the codebook state the timed loop left behind is bit-identical on every rank;
+    (2) a small problem run sharded for 2 steps equals rank 0's single-process full-batch run of the same problem
+        (indices identical up to near-ties counted by value, codebooks to 1e-5 relative -- fp32 summation order)."""
+    out = {}
+    cs = state_checksum(torch, layers)
+    gathered = [torch.empty_like(cs) for _ in range(world)]
+    dist.all_gather(gathered, cs)
+    out["ranks_identical"] = bool(all(torch.equal(gathered[0], g) for g in gathered))
+    # (2) small sharded-vs-single comparison: RVQ 4 x 1024, 8192 windows in total
+    cfg = dict(kind="rvq", S=4, K=1024, D=64, B=8192, T=10)
+    gen = torch.Generator(device=dev).manual_seed(4321)
+    zfull = torch.randn((cfg["B"], cfg["D"], cfg["T"]), generator=gen, device=dev).mul_(0.5)
+    lo, hi = vqb200.dist.shard_bounds(cfg["B"], rank, world)
+    mod_s, lay_s = build_module(vqb200, torch, cfg, dev, seed=7)
+    with torch.no_grad():
+        for _ in range(2):
+            mod_s(zfull[lo:hi].contiguous())
+    idx_s = mod_s.last_indices.clone()                               # [S, B/world, T] of step 2
+    w_sharded = torch.cat([l.embedding.weight.detach().reshape(-1) for l in lay_s])
+    torch.cuda.synchronize()
+    vqb200.dist.disable()
+    ok = torch.ones(2, device=dev)
+    if rank == 0:
+        mod_f, lay_f = build_module(vqb200, torch, cfg, dev, seed=7)
+        with torch.no_grad():
+            for _ in range(2):
+                mod_f(zfull)
+        w_full = torch.cat([l.embedding.weight.detach().reshape(-1) for l in lay_f])
+        rel = float(((w_sharded - w_full).abs().max() / w_full.abs().max()).item())
+        flips = int((mod_f.last_indices[:, lo:hi] != idx_s).sum().item())
+        out["sharded_vs_single"] = {"windows": cfg["B"], "steps": 2, "codebook_max_rel_err": rel,
+                                    "index_flips_rank0_shard": flips, "rows_rank0_shard": int(idx_s.numel()),
+                                    "ok": bool(rel < 1e-4 and flips <= idx_s.numel() // 1000)}
+        ok[0] = 1.0 if out["sharded_vs_single"]["ok"] else 0.0
+    vqb200.dist.enable(peer=exchange, uniform_shards=True)
+    return out
+
+
 def run_gpu(args):
     import torch
     import vqb200
@@ -183,15 +331,22 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-        vqb200.dist.enable(peer=args.exchange, uniform_shards=True)      # every rank runs the same shapes
+    numa = bind_to_gpu_numa(torch, local) if world > 1 else "single process: not bound"
     cfg = dict(WORKLOADS[args.workload])
     if args.windows:
         cfg["B"] = args.windows
-    K, D, S, B, T = cfg["K"], cfg["D"], cfg["S"], cfg["B"], cfg["T"]
+    strong = args.scaling == "strong"
+    B_total = cfg["B"] if strong else cfg["B"] * world
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        # equal shards let the launch-bound shapes take the single-launch kernels with the exchange inside
+        vqb200.dist.enable(peer=args.exchange, uniform_shards=(B_total % world == 0))
+    lo, hi = vqb200.dist.shard_bounds(B_total, rank, world) if world > 1 else (0, B_total)
+    K, D, S, T = cfg["K"], cfg["D"], cfg["S"], cfg["T"]
+    B = hi - lo                              # this rank's windows
     N = B * T
+    N_total = B_total * T
     peaks = load_peaks()
     mod, layers = build_module(vqb200, torch, cfg, dev)
     gen = torch.Generator(device=dev).manual_seed(1237 + rank)
@@ -236,7 +391,11 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_per_step = ms / args.steps
-    value = N * world / (ms_per_step * 1e-3)
+    value = N_total / (ms_per_step * 1e-3)
+    verify = None
+    if world > 1 and not args.no_verify:
+        import torch.distributed as dist
+        verify = verify_multi_gpu(torch, vqb200, dist, dev, rank, world, layers, args.exchange)
 
     # ---- end-to-end: pinned host input -> H2D -> fwd+EMA+bwd -> D2H of loss / perplexity / indices ----
     # Every step copies ITS input from pinned host memory and reads ITS result back; the copy of step i+1 is issued on
@@ -291,10 +450,11 @@ def run_gpu(args):
             t = torch.tensor([ems], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
-        e2e = {"value": N * world / (ems / n_e2e * 1e-3), "unit": UNIT,
+        e2e = {"value": N_total / (ems / n_e2e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(z_host.numel() * 4), "d2h_bytes_per_step": int(idx_host.numel() * 4 + 8),
                "ms_per_step": ems / n_e2e, "steps": n_e2e,
-               "note": "H2D of step i+1 overlaps compute of step i (double-buffered); PCIe-bound"}
+               "h2d_GBps_per_rank": z_host.numel() * 4 / (ems / n_e2e * 1e-3) / 1e9, "numa": numa,
+               "note": "per-rank bytes; H2D of step i+1 overlaps compute of step i (double-buffered); PCIe-bound"}
         del z_host, idx_host, z_bufs
     except Exception as ex:  # pragma: no cover
         e2e = {"error": repr(ex)}
@@ -344,6 +504,39 @@ def run_gpu(args):
         roof["step_floor_ms"] = floor * 1e3
         roof["step_frac_of_floor"] = floor * 1e3 / ms_per_step
 
+    # ---- N > 1, strong scaling: a short weak-scaling measurement (1 M windows PER GPU) for other_workloads ----
+    weak = None
+    if world > 1 and strong and not args.no_extras:
+        import torch.distributed as dist
+        try:
+            del z, g, zr
+            torch.cuda.empty_cache()
+            Bw = cfg["B"]
+            zw = torch.randn((Bw, D, T), generator=gen, device=dev).mul_(0.5).requires_grad_(True)
+            gw = torch.randn((Bw, D, T), generator=gen, device=dev)
+
+            def wstep():
+                zw.grad = None
+                lw, qw, _ = mod(zw)
+                torch.autograd.backward([qw, lw], [gw, one])
+            for _ in range(3):
+                wstep()
+            barrier()
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record()
+            for _ in range(3):
+                wstep()
+            w1.record()
+            barrier()
+            t = torch.tensor([w0.elapsed_time(w1)], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wms = float(t.item()) / 3
+            weak = {"scaling": "weak", "windows_per_gpu": Bw, "ms_per_step": wms,
+                    "vectors_per_s": Bw * T * world / (wms * 1e-3), "steps": 3}
+            del zw, gw
+        except Exception as ex:  # pragma: no cover
+            weak = {"error": repr(ex)}
+
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -362,21 +555,22 @@ def run_gpu(args):
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: ResidualVQ S={S} K={K} D={D} EMA training step (fwd+EMA+bwd), "
-                               f"z [{B},{D},{T}] fp32 per GPU = {N} vectors/GPU, batch sharded on dim 0, per-stage "
-                               f"EMA stats summed across ranks" if cfg["kind"] == "rvq" else
-                               f"{args.workload}: VectorQuantizer K={K} D={D} EMA training step, z [{B},{D},{T}] per GPU",
-                   "vectors_per_gpu": N, "parallelism": f"dp{world}",
+        "config": {"workload": workload_text(args.workload, cfg, B_total, world),
+                   "vectors_total": N_total, "vectors_per_gpu": N, "parallelism": f"dp{world}",
                    "stats_exchange": vqb200.dist.peer_status() if world > 1 else "none (single GPU)",
                    "l2": "inputs larger than L2 (2.56 GB per tensor per GPU)" if N * D * 4 > 256e6 else "L2 not flushed (small input)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roof, "cpu_baseline": cpu,
         "loss": float(loss.item()), "perplexity": float(met["perplexity"].item()),
     }
+    if verify is not None:
+        out["verify"] = verify
     if extras:
         out["other_workloads"] = extras
+    if weak is not None:
+        out.setdefault("other_workloads", {})["cfg3_weak_scaling"] = weak
     print(json.dumps(out))
     if world > 1:
         import torch.distributed as dist
@@ -434,59 +628,81 @@ def run_extras(torch, vqb200, dev, peaks):
         g1s = vqb200.GraphedQuantizerStep(mod, z.detach())
         ms = timeit(lambda: g1s(z.detach(), g), 50)
         res["cfg1_ema_k1024_n40960_cuda_graph"] = {"us_per_step": ms * 1e3, "vectors_per_s": cfg["B"] * cfg["T"] / (ms * 1e-3)}
-        # cfg4: FSQ / LFQ elementwise stage, 1 048 576 windows x 10
-        B = 1_048_576
-        ze = 2.0 * torch.randn(B, 4, 10, device=dev)
+        # cfg4 (BASELINE.json configs[3]): FSQ / LFQ batch sweep 4096 -> 1 M windows x 10 frames.
+        # "elementwise" = the round / sign + index-pack stage alone on the post-projection tensor (40 / 88 algorithmic
+        # bytes per vector); "module" = the whole module with both 1x1 projections fused in (8D + 4d + 8 bytes forward,
+        # 20D + 8d + 8 forward + backward).  Small batches are launch-bound: read them as microseconds.
         basis = torch.tensor([1, 8, 40, 200], dtype=torch.int32, device=dev)
-        ms = timeit(lambda: vqb200.fsq_round(ze, basis, 1000), 10)
-        n = B * 10
-        res["cfg4_fsq_elementwise_n10m"] = {"vectors_per_s": n / (ms * 1e-3), "GBps_algorithmic": n * 40 / (ms * 1e-3) / 1e9,
-                                            "frac_of_hbm": n * 40 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
-        zl = torch.randn(B, 10, 10, device=dev)
-        ms = timeit(lambda: vqb200.lfq_sign(zl, 0.1), 10)
-        res["cfg4_lfq_elementwise_n10m"] = {"vectors_per_s": n / (ms * 1e-3), "GBps_algorithmic": n * 88 / (ms * 1e-3) / 1e9,
-                                            "frac_of_hbm": n * 88 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
-        del ze, zl
-        # cfg4, whole modules with the 1x1 projections fused in: 8D + 4d + 8 bytes / vector forward
-        z4 = 2.0 * torch.randn(B, 64, 10, device=dev)
-        g4 = torch.randn(B, 64, 10, device=dev)
-        for name, m4, dq in (("fsq", vqb200.FSQ([8, 5, 5, 5], 64, 64).to(dev), 4), ("lfq", vqb200.LFQ(64, 10).to(dev), 10)):
-            def f4():
-                with torch.no_grad():
-                    m4(z4)
-            ms = timeit(f4, 10)
-            byts = n * (8 * 64 + 4 * dq + 8)
-            res[f"cfg4_{name}_module_fused_fwd_n10m"] = {"ms": ms, "vectors_per_s": n / (ms * 1e-3), "GBps_algorithmic": byts / (ms * 1e-3) / 1e9,
-                                                         "frac_of_hbm": byts / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
-            zz4 = z4.clone().requires_grad_(True)
+        sweep = {}
+        for B4 in (4096, 16384, 65536, 262144, 1048576):
+            n = B4 * 10
+            reps = 20 if B4 <= 65536 else 8
+            row = {"vectors": n}
+            ze = 2.0 * torch.randn(B4, 4, 10, device=dev)
+            ms = timeit(lambda: vqb200.fsq_round(ze, basis, 1000), reps)
+            row["fsq_elementwise"] = {"us": ms * 1e3, "vectors_per_s": n / (ms * 1e-3), "frac_of_hbm": n * 40 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+            zl = torch.randn(B4, 10, 10, device=dev)
+            ms = timeit(lambda: vqb200.lfq_sign(zl, 0.1), reps)
+            row["lfq_elementwise"] = {"us": ms * 1e3, "vectors_per_s": n / (ms * 1e-3), "frac_of_hbm": n * 88 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+            del ze, zl
+            z4 = 2.0 * torch.randn(B4, 64, 10, device=dev)
+            g4 = torch.randn(B4, 64, 10, device=dev)
+            for name, m4, dq in (("fsq", vqb200.FSQ([8, 5, 5, 5], 64, 64).to(dev), 4), ("lfq", vqb200.LFQ(64, 10).to(dev), 10)):
+                def f4():
+                    with torch.no_grad():
+                        m4(z4)
+                ms = timeit(f4, reps)
+                byts = n * (8 * 64 + 4 * dq + 8)
+                row[f"{name}_module_fwd"] = {"us": ms * 1e3, "vectors_per_s": n / (ms * 1e-3),
+                                             "frac_of_hbm": byts / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+                zz4 = z4.clone().requires_grad_(True)
 
-            def fb4():
-                zz4.grad = None
-                loss, out, _ = m4(zz4)
-                if loss.requires_grad:
-                    torch.autograd.backward([out, loss], [g4, one])
-                else:
-                    out.backward(g4)
-            ms = timeit(fb4, 5)
-            byts = n * (20 * 64 + 8 * dq + 8)
-            res[f"cfg4_{name}_module_fused_fwdbwd_n10m"] = {"ms": ms, "vectors_per_s": n / (ms * 1e-3), "GBps_algorithmic": byts / (ms * 1e-3) / 1e9,
-                                                            "frac_of_hbm": byts / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
-            del zz4
-        del z4, g4
-        # cfg5 sweep points (assignment kernel K1 alone; N bounded so that the default run stays short).
-        # D = 64 / 128 / 256 run the tcgen05 path, D = 512 the exact CUDA-core path.
-        for (K5, D5, N5) in ((512, 64, 4_194_304), (4096, 64, 2_097_152), (16384, 64, 1_048_576), (65536, 64, 262_144),
-                            (4096, 128, 1_048_576), (4096, 256, 524_288), (4096, 512, 65_536)):
-            torch.manual_seed(5)
-            w5 = torch.randn(K5, D5, device=dev)
+                def fb4():
+                    zz4.grad = None
+                    loss, out, _ = m4(zz4)
+                    if loss.requires_grad:
+                        torch.autograd.backward([out, loss], [g4, one])
+                    else:
+                        out.backward(g4)
+                ms = timeit(fb4, max(3, reps // 2))
+                byts = n * (20 * 64 + 8 * dq + 8)
+                row[f"{name}_module_fwdbwd"] = {"us": ms * 1e3, "vectors_per_s": n / (ms * 1e-3),
+                                                "frac_of_hbm": byts / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+                del zz4
+            del z4, g4
+            sweep[f"B{B4}"] = row
+        res["cfg4_fsq_lfq_batch_sweep"] = sweep
+        # cfg5 (BASELINE.json configs[4]): EMA-VQ forward + EMA update (train mode, no backward) on N = 4 194 304 vectors
+        # [N, D, 1], codebook N(0,1), the full K x D grid.  floor = max(flops / bf16 peak, (8D + 4) bytes / HBM) per
+        # SURVEY.md §8(d); frac = floor / measured.  (One warm-up + 2 timed steps per point.)
+        grid = {}
+        N5 = 4_194_304
+        for D5 in (64, 128, 256, 512):
             z5 = torch.randn(N5, D5, 1, device=dev)
-            st5 = vqb200.QuantizerState(K5, D5, dev)
-            ms = timeit(lambda: vqb200.vq_assign(z5, w5, st5), 3, warm=2)
-            fl = 2.0 * N5 * K5 * D5
-            res[f"cfg5_assign_k{K5}_d{D5}"] = {"n": N5, "ms": ms, "vectors_per_s": N5 / (ms * 1e-3),
-                                               "TFLOPs": fl / (ms * 1e-3) / 1e12,
-                                               "frac_of_bf16_peak": fl / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"]}
-            del w5, z5, st5
+            for K5 in (512, 1024, 2048, 4096, 8192, 16384, 32768, 65536):
+                try:
+                    torch.manual_seed(5)
+                    m5 = vqb200.VectorQuantizer(K5, D5, use_ema=True).to(dev).train()
+                    with torch.no_grad():
+                        m5.embedding.weight.normal_(0, 1.0)
+                        m5.ema_w.copy_(m5.embedding.weight)
+                        m5.ema_cluster_size.fill_(1.0)
+
+                    def s5():
+                        with torch.no_grad():
+                            m5(z5)
+                    ms = timeit(s5, 2, warm=1)
+                    fl = 2.0 * N5 * K5 * D5
+                    floor_ms = max(fl / (peaks["bf16_tflops"] * 1e12), N5 * (8 * D5 + 4) / (peaks["hbm_gbs"] * 1e9)) * 1e3
+                    grid[f"k{K5}_d{D5}"] = {"ms": ms, "vectors_per_s": N5 / (ms * 1e-3), "TFLOPs": fl / (ms * 1e-3) / 1e12,
+                                            "bound": "tensor" if fl / (peaks["bf16_tflops"] * 1e12) * 1e3 >= floor_ms * 0.999 else "hbm",
+                                            "frac_of_roofline": floor_ms / ms}
+                    del m5
+                except Exception as ex:  # pragma: no cover
+                    grid[f"k{K5}_d{D5}"] = {"error": repr(ex)[:200]}
+            del z5
+            torch.cuda.empty_cache()
+        res["cfg5_ema_vq_fwd_ema_n4m_grid"] = grid
     except Exception as ex:  # pragma: no cover
         res["error"] = repr(ex)
     return res
@@ -503,9 +719,9 @@ def run_reference(args):
     out = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: ResidualVQ S={S} K={K} D={D} EMA training step (fwd+EMA+bwd), "
-                               f"reference algorithm on host CPU cores, bounded sample", "parallelism": "cpu"},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_text(args.workload, cfg, B if args.scaling == "strong" else B * world, world),
+                   "parallelism": "host cpu", "sample": r["sample"]},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -524,6 +740,10 @@ def main():
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="transport of the per-stage EMA statistics at N > 1: peer memory fused into the finalize "
                          "kernels (csrc/peer.cu) or an NCCL all-reduce; auto = peer when the node allows it")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): the workload's windows are the TOTAL, sharded over the GPUs (BASELINE.json "
+                         "configs[2]); weak: that many windows per GPU")
+    ap.add_argument("--no-verify", action="store_true", help="skip the multi-GPU correctness bits (N > 1)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()

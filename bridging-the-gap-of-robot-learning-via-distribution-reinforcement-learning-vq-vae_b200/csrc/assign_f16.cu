@@ -592,11 +592,10 @@ vq_assign_f16_kernel(const Params p) {
         // The arrive below hands the accumulator back to the MMA issuer and (through MMA(it+2) -> empty -> producer) lets
         // this tile's meta slot be refilled.  ptxas hoists a bare arrive above the last chunk's math; with the row-major
         // layout (the converter's bank-conflicted loads slow the epilogue warps down) that was measured to mis-assign
-        // ~0.04 % of the rows, run to run different.  Making the arrive data-dependent on t1/t2 closes it.
+        // ~0.04 % of the rows, run to run different.  arrive_after() orders the arrive behind a store of t1/t2.
         tc_fence_before();
         __syncwarp();
-        // (the comparison is always true; it makes the arrive data-dependent on the finished math for ptxas as well)
-        if (lane == 0 && (__float_as_uint(t1) ^ __float_as_uint(t2)) != 0x7fc12345u) mbar_arrive(smem_u32(tempty + as * RT + rt));
+        if (lane == 0) arrive_after(smem_u32(tempty + as * RT + rt), smem_u32(tmem_slot + 1), t1, t2);
         tr.merge(t1, t2, j);
       }
       float thr, mag;
@@ -765,8 +764,8 @@ vq_assign_f16_res_kernel(const Params p) {
         epilogue_tile(taddr, sM + (size_t)j * F16_META_FLOATS, ri.x, p.dbg, t1, t2);
         tc_fence_before();
         __syncwarp();
-        // same data dependency as in the streaming kernel: the accumulator is handed back only after its values were used
-        if (lane == 0 && (__float_as_uint(t1) ^ __float_as_uint(t2)) != 0x7fc12345u) mbar_arrive(smem_u32(tempty + g * 2 + st));
+        // as in the streaming kernel: the accumulator is handed back only after its values were used
+        if (lane == 0) arrive_after(smem_u32(tempty + g * 2 + st), smem_u32(tmem_slot + 1), t1, t2);
         tr.merge(t1, t2, j);
         if (stamps && q == 0 && lane == 0 && cnt < 1024) {
           long long* e = stamps + (1 + g) * 1024 * 4 + cnt * 4;

@@ -358,9 +358,7 @@ vq_assign_tc_kernel(const Params p) {
         }
         tc_fence_before();
         __syncwarp();
-        // always true; makes the arrive data-dependent on the finished math (ptxas otherwise hoists it above the last
-        // chunk's shared-memory reads -- see assign_f16.cu)
-        if (lane == 0 && (__float_as_uint(t1) ^ __float_as_uint(t2)) != 0x7fc12345u) mbar_arrive(smem_u32(tempty + as * RT + rt));
+        if (lane == 0) arrive_after(smem_u32(tempty + as * RT + rt), smem_u32(tmem_slot + 1), t1, t2);
         // merge the tile-local top-2 into the row's running top-2
         const int ti = j * BN + (int)(__float_as_uint(t1) & 127u);
         if (t1 > g1) { g2 = fmaxf(g1, t2); g1 = t1; gi = ti; }

@@ -2,11 +2,12 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace vqb200 {
 namespace ptx {
 
-constexpr unsigned SPIN_LIMIT = 1u << 20;   // bounded waits: a protocol bug traps instead of hanging the GPU
+constexpr unsigned SPIN_LIMIT = 1u << 24;   // bounded waits: a protocol bug traps instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -19,16 +20,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" :: "r"(bar), "r"(bytes) : "memory");
 }
-// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint, in ns,
-// expires) instead of returning at once -- a plain spin loop of waiting warps was measured to burn 38 % of the SM's
-// issue slots in the assignment kernel (BRA / ISETP / IADD3 / SYNCS / YIELD in the ncu source page)
-#ifndef VQB200_MBAR_HINT_NS
-#define VQB200_MBAR_HINT_NS 20000
-#endif
+// Plain try_wait (the hardware parks the thread for an implementation-defined, short time).  A variant with an explicit
+// suspend-time hint (20 us) was measured: ~2 % faster, but with it the streaming assignment kernel hung reproducibly at
+// K >= 32 768 right after the EMA kernels (producer and MMA-issuer threads parked inside try_wait and never resumed,
+// every mbarrier idle) -- removed.
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
-               : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)VQB200_MBAR_HINT_NS) : "memory");
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
 // non-blocking probe (mbarrier.test_wait never suspends the thread)
@@ -38,10 +37,23 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
                : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code, uint32_t dump_base = 0, int dump_n = 0) {
   unsigned spins = 0;
+  long long t0 = 0;
   while (!mbar_try(bar, parity)) {
-    if (++spins > SPIN_LIMIT) { if (err) atomicExch(err, code); __trap(); }
+    if (spins == 0) t0 = clock64();
+    ++spins;
+    if (spins == SPIN_LIMIT / 4 && (threadIdx.x & 31) == 0)      // report every stuck role before the first one traps
+    {
+      printf("vqb200: mbarrier wait %d stuck for %lld cycles (block %d, warp %d, parity %u)\n", code, clock64() - t0,
+             (int)blockIdx.x, (int)(threadIdx.x >> 5), parity);
+      for (int i = 0; i < dump_n; ++i) {
+        unsigned long long w;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(w) : "r"(dump_base + 8 * i));
+        printf("vqb200:   block %d bar[%d] = %016llx\n", (int)blockIdx.x, i, w);
+      }
+    }
+    if (spins > SPIN_LIMIT) { if (err) atomicExch(err, code); __trap(); }
   }
 }
 // 1-D bulk-TMA copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)

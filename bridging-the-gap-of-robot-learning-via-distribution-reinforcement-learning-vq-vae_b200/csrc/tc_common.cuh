@@ -38,6 +38,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                : "r"(taddr) : "memory");
 }
+// mbarrier arrive that ptxas cannot hoist above the math producing (a, b): the values are first stored to a shared
+// sink word, and the arrive (release semantics) is ordered after that store.  A bare arrive was measured to be scheduled
+// before the last chunk's math of the epilogue (mis-assigned rows, run to run different, see assign_f16.cu); an
+// always-true predicate on the values "works" until the bit pattern it excludes turns up (it did: a lost arrive = hang).
+__device__ __forceinline__ void arrive_after(uint32_t bar, uint32_t sink, float a, float b) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(sink), "r"(__float_as_uint(a) ^ __float_as_uint(b)) : "memory");
+  mbar_arrive(bar);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 128-byte rows, 8-row groups 1024 B apart.

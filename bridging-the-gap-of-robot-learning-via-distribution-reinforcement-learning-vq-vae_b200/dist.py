@@ -199,12 +199,34 @@ def _close_peer() -> None:
 
 def disable() -> None:
     global _GROUP, _ENABLED, _PEER_STATUS, _UNIFORM
+    _AGREED.clear()
     _close_peer()
     _GROUP, _ENABLED, _PEER_STATUS, _UNIFORM = None, False, "off", False
 
 
 def uniform_shards() -> bool:
     return _UNIFORM and enabled()
+
+
+_AGREED = {}
+
+
+def agree(key, local: bool) -> bool:
+    """Collective AND of a per-rank, device-probed decision, cached per `key` (one tiny all-reduce and host read the
+    first time a key is seen).  Ranks must ask for a new key in the same step -- which `uniform_shards` promises.
+    Used for choices that change the barrier / slot pattern of the peer exchange (the single-launch ResidualVQ kernel):
+    `cudaOccupancyMaxActiveClusters` differs between GPUs of one node, so two ranks can disagree near the size limit."""
+    k = (id(_GROUP), key)
+    if k not in _AGREED:
+        if not enabled():
+            return bool(local)
+        dev = _PEER.device if _PEER is not None else (torch.device("cuda", torch.cuda.current_device())
+                                                      if torch.cuda.is_available() and torch_dist.get_backend(_GROUP) == "nccl"
+                                                      else torch.device("cpu"))
+        t = torch.tensor([1 if local else 0], dtype=torch.int32, device=dev)
+        torch_dist.all_reduce(t, op=torch_dist.ReduceOp.MIN, group=_GROUP)
+        _AGREED[k] = bool(int(t.item()))
+    return _AGREED[k]
 
 
 def peer_exchange() -> Optional[PeerExchange]:

@@ -173,8 +173,11 @@ class _RVQFn(torch.autograd.Function):
         if (not fused and cfg.algo == _lib.ASSIGN_AUTO and N > 0 and px is not None and px.device == dev
                 and _dist.uniform_shards()):
             with torch.cuda.device(dev):
-                fused_peer = (bool(lib.vqb200_rvq_small_peer_eligible(N, C, S, Ks))
-                              and int(lib.vqb200_rvq_small_stats_floats(S, Ks)) * 4 <= px.slot_bytes)
+                local_ok = (bool(lib.vqb200_rvq_small_peer_eligible(N, C, S, Ks))
+                            and int(lib.vqb200_rvq_small_stats_floats(S, Ks)) * 4 <= px.slot_bytes)
+            # the eligibility probe is device-local (co-resident clusters differ between GPUs): every rank must take
+            # the same path, or slot parity and barrier pattern of the exchange diverge
+            fused_peer = _dist.agree(("rvq_small_peer", N, C, S, tuple(int(k) for k in Ks)), local_ok)
             fused = fused_peer
         if fused:
             with torch.cuda.device(dev):

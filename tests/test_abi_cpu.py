@@ -162,3 +162,33 @@ def test_token_layout_and_file_format_need_no_gpu(tmp_path):
     assert back.spec == hy and torch.equal(back.data, tb.data)
     with pytest.raises(RuntimeError):
         tokens.decode(vqb200.HybridVQ(64, [8, 5, 5, 5], 512), back)      # CPU tokens: no CPU path
+
+
+def test_staged_reference_is_unmodified_when_present():
+    """oracle/_ref (git-ignored, staged by build() from /root/reference) must hold byte-identical copies."""
+    import hashlib, json, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref, "MANIFEST.json")):
+        import pytest
+        pytest.skip("oracle/_ref not staged in this checkout")
+    m = json.load(open(os.path.join(ref, "MANIFEST.json")))
+    assert "models/vqvae.py" in m["files"] and "scripts/train_ablation.py" in m["files"]
+    for rel, digest in m["files"].items():
+        assert hashlib.sha256(open(os.path.join(ref, rel), "rb").read()).hexdigest() == digest, rel
+        src = os.path.join(m["source"], rel)
+        if os.path.exists(src):          # only in the build container
+            assert hashlib.sha256(open(src, "rb").read()).hexdigest() == digest, f"{rel} differs from the reference tree"
+
+
+def test_reference_arm_runs_the_staged_reference_modules():
+    """bench.py's CPU arm: the unmodified reference ResidualVQ (torch CPU) on a tiny sample; kind == 'reference'."""
+    import os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "models", "vqvae.py")):
+        import pytest
+        pytest.skip("oracle/_ref not staged in this checkout")
+    sys.path.insert(0, root)
+    import bench
+    r = bench.cpu_reference_arm(dict(kind="rvq", S=2, K=64, D=64, B=64, T=10), steps=1, warmup=1, chunk_vectors=640)
+    assert r["kind"] == "reference" and r["value"] > 0 and r["cores"] >= 1

@@ -4,6 +4,7 @@
 scripts/deployment/export_motion.py:51-71."""
 import io
 
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -313,3 +314,55 @@ def test_ddp_trainer_whole_step_cuda_graph_matches_eager(tmp_path):
     assert all(v == v and abs(v) < 1e9 for v in h["train_loss"])
     sd = torch.load(tmp_path / "h" / "h_hybrid_teacher_seed_7_final.pth", map_location=DEV)
     assert float(sd["quantizer.vq.layers.0.ema_cluster_size"].sum()) > 0
+
+
+def _run_train_ablation(work, script, models_dir, root):
+    """One epoch of the staged, byte-identical scripts/train_ablation.py in `work` with `models` -> models_dir."""
+    import json, os, subprocess, sys
+    (work / "scripts").mkdir(parents=True)
+    (work / "scripts" / "train_ablation.py").write_bytes(open(script, "rb").read())
+    os.symlink(models_dir, work / "models")          # found through the script's own sys.path.append(<parent of scripts>)
+    (work / "data" / "processed").mkdir(parents=True)
+    rng = np.random.default_rng(0)
+    np.save(work / "data" / "processed" / "g1_train.npy", rng.standard_normal((4096, 10, 29)).astype(np.float32))
+    np.save(work / "data" / "processed" / "human_train.npy", rng.standard_normal((4096, 10, 126)).astype(np.float32))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""), CUDA_VISIBLE_DEVICES="0")
+    r = subprocess.run([sys.executable, "scripts/train_ablation.py", "--mode", "teacher", "--arch", "resnet_no_down",
+                        "--method", "ema", "--window", "10", "--epochs", "1", "--batch_size", "4096", "--seed", "42"],
+                       cwd=work, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "Success" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    hist = json.load(open(work / "results" / "log_Exp_resnet_no_down_W10_teacher_seed_42.json"))
+    sd = torch.load(work / "checkpoints" / "Exp_resnet_no_down_W10_ema_teacher_seed_42_final.pth", map_location="cpu")
+    return hist["train_loss"][0], hist["val_recon"][0], sd
+
+
+def test_unmodified_train_ablation_script(tmp_path):
+    """The reference's OWN training script (scripts/train_ablation.py, staged byte-identical under oracle/_ref by
+    build(); sha256 in MANIFEST.json) run for one epoch on the survey's synthetic data, twice on the
+    same GPU: against this repo's drop-in `models/vqvae.py`, and against the reference's own `models/` package.
+      * sum(ema_cluster_size) = 368.6 = 0.01 * 36 860 vectors: exact arithmetic, 1e-4 everywhere;
+      * train_loss[0] (27.658796 for the reference on CPU) is a chaotic quantity: the first EMA update at the
+        U(+-1/K) init divides ema_w ~ N(0,1) by counts of one or two vectors, so a single benign near-tie flip (the
+        reference's own distances contain exact fp32 ties there) moves a codeword by O(50) and the loss
+        by ~0.07.  Measured on B200: reference modules on the GPU 28.12, drop-in 27.02 / 28.31 in two runs (stock
+        cuDNN encoder rounding decides the ties) -- all within 3 % of the CPU value.  Tolerance 5 % against the CPU
+        known answer, for the drop-in AND for the reference itself on the same GPU;
+      * val_recon[0] (1.153451 on CPU; 1.1532 reference on GPU, 1.1462 drop-in): 2 %."""
+    import hashlib, json, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "oracle", "_ref")
+    script = os.path.join(ref, "scripts", "train_ablation.py")
+    if not os.path.exists(script):
+        pytest.skip("oracle/_ref is not staged (run __graft_entry__.build() where /root/reference exists)")
+    manifest = json.load(open(os.path.join(ref, "MANIFEST.json")))
+    assert hashlib.sha256(open(script, "rb").read()).hexdigest() == manifest["files"]["scripts/train_ablation.py"]
+    ours = _run_train_ablation(tmp_path / "dropin", script, os.path.join(root, "models"), root)
+    theirs = _run_train_ablation(tmp_path / "reference", script, os.path.join(ref, "models"), root)
+    cs_o, cs_r = float(ours[2]["quantizer.ema_cluster_size"].sum()), float(theirs[2]["quantizer.ema_cluster_size"].sum())
+    print("train_ablation.py, drop-in   : train_loss", ours[0], "val_recon", ours[1], "sum(ema_cluster_size)", cs_o)
+    print("train_ablation.py, reference : train_loss", theirs[0], "val_recon", theirs[1], "sum(ema_cluster_size)", cs_r)
+    assert sorted(ours[2].keys()) == sorted(theirs[2].keys())
+    assert abs(cs_o - cs_r) / cs_r < 1e-4 and abs(cs_o - 368.6) / 368.6 < 1e-4
+    for got in (ours, theirs):
+        assert abs(got[0] - 27.658796) / 27.658796 < 0.05
+        assert abs(got[1] - 1.153451) / 1.153451 < 0.02
