@@ -83,5 +83,6 @@ __device__ __forceinline__ void info_update(float* info, float ee_k, bool nonfin
 
 // builds the fp16 filter image + info[2] from the refreshed E and split image (ema.cu); no-op unless D == 64 and image != NULL
 int launch_image_f16(const float* E, long long K, long long D, void* image, float* info, cudaStream_t stream);
+int preload_image_f16();
 
 }  // namespace vqb200

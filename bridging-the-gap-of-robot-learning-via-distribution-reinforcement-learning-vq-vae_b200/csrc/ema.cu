@@ -285,6 +285,14 @@ codebook_image_f16_kernel(const float* __restrict__ E, int K, unsigned char* __r
   if (info && tid == 0 && bad) atomicExch(reinterpret_cast<int*>(info + 1), __float_as_int(1.0f));
 }
 
+// kernels are loaded lazily and a first load may synchronise the context: callers that are about to spin on a peer
+// (peer.cu) load this one up front
+int preload_image_f16() {
+  cudaFuncAttributes fa;
+  VQ_CUDA(cudaFuncGetAttributes(&fa, codebook_image_f16_kernel));
+  return VQB200_OK;
+}
+
 int launch_image_f16(const float* E, long long K, long long D, void* image, float* info, cudaStream_t stream) {
   if (!image || !img_has_f16(D)) return VQB200_OK;
   VQ_CHECK_ARG((reinterpret_cast<uintptr_t>(E) & 15) == 0, VQB200_EALIGN, "codebook image: E must be 16-byte aligned");

@@ -211,6 +211,7 @@ int vqb200_peer_barrier(uint32_t* const* peer_flags, int32_t rank, int32_t world
       VQ_CUDA(cudaFuncGetAttributes(&fa, peer::finalize_cs_kernel));
       VQ_CUDA(cudaFuncGetAttributes(&fa, peer::finalize_w_kernel));
       VQ_CUDA(cudaFuncGetAttributes(&fa, peer::barrier_kernel));
+      { const int rc2 = preload_image_f16(); if (rc2 != VQB200_OK) return rc2; }
       loaded.store(1);
     }
   }
