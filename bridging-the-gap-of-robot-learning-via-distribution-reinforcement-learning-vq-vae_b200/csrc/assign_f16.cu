@@ -144,11 +144,14 @@ __device__ __forceinline__ StagePlan stage_plan(const Params& p, long long n0, i
 // ------------------------------------------------------------------------------------------
 // converter: one row tile, raw fp32 rows (already in `buf` for the staged modes) -> fp16 A operand + row info, in place
 // ------------------------------------------------------------------------------------------
+template <class Wait>
 __device__ __forceinline__ void convert_tile(const Params& p, unsigned char* buf, long long n0, int rows, int row, int kp,
-                                             bool lead) {
+                                             Wait wait_for_rows) {
   const float* raw = reinterpret_cast<const float*>(buf);
   const bool fuse = p.r_out != nullptr;
   float v[D];
+  const float4* __restrict__ q4 = reinterpret_cast<const float4*>(p.prev_E + (size_t)kp * D);
+  wait_for_rows();
   if (row < rows) {
     const long long n = n0 + row;
     if (p.stage_mode == STG_ROWS) {
@@ -169,16 +172,36 @@ __device__ __forceinline__ void convert_tile(const Params& p, unsigned char* buf
 #pragma unroll
       for (int k = 0; k < D; ++k) v[k] = __ldg(src + (long long)k * p.z.sC);
     }
-    if (fuse) {                              // same three roundings as the stand-alone residual kernel
-      const float4* q4 = reinterpret_cast<const float4*>(p.prev_E + (size_t)kp * D);
+    if (fuse) {
+      // r = x - (x + (q - x)): the same three roundings as the stand-alone residual kernel.  The new residual goes
+      // straight from the registers to r_out (a warp's 32 consecutive rows cover whole samples, so the 4-byte stores of
+      // one component merge into full sectors in L2); staging it in shared memory for a bulk store cost two more
+      // converter barriers and the store's read latency per row tile and made the converter the slowest role
+      // (12 k cycles per job instead of 3.4 k: stages >= 1 took 4.05 ms instead of 3.0 ms per 10 M x 1024).
+      float* __restrict__ dst = p.r_out + ((p.stage_mode == STG_ROWS) ? n * D : (n / p.z.T) * (long long)(D * p.z.T) + (n % p.z.T));
+      const int so = (p.stage_mode == STG_ROWS) ? 1 : (int)p.z.T;
+      // the codeword in two batches of 8 loads (all of a batch in flight together: the stores below may not be
+      // reordered with loads, so a load per 4 components would cost 16 L2 round trips per row tile)
 #pragma unroll
-      for (int c = 0; c < D / 4; ++c) {
-        const float4 q = __ldg(q4 + c);
-        const float qv[4] = {q.x, q.y, q.z, q.w};
+      for (int h = 0; h < 2; ++h) {
+        float4 q[D / 8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float x = v[4 * c + e];
-          v[4 * c + e] = __fsub_rn(x, __fadd_rn(x, __fsub_rn(qv[e], x)));
+        for (int c = 0; c < D / 8; ++c) q[c] = __ldg(q4 + h * (D / 8) + c);
+#pragma unroll
+        for (int c8 = 0; c8 < D / 8; ++c8) {
+          const int c = h * (D / 8) + c8;
+          const float qv[4] = {q[c8].x, q[c8].y, q[c8].z, q[c8].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x = v[4 * c + e];
+            v[4 * c + e] = __fsub_rn(x, __fadd_rn(x, __fsub_rn(qv[e], x)));
+          }
+          if (p.stage_mode == STG_ROWS) {
+            *reinterpret_cast<float4*>(dst + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dst[(4 * c + e) * so] = v[4 * c + e];
+          }
         }
       }
     }
@@ -187,33 +210,6 @@ __device__ __forceinline__ void convert_tile(const Params& p, unsigned char* buf
     for (int k = 0; k < D; ++k) v[k] = 0.f;
   }
   converter_sync();                          // every raw read of this buffer is done
-  if (fuse) {
-    // write the new residual back in the raw layout and stream the slab to r_out before converting in place
-    if (row < rows) {
-      float* rawW = reinterpret_cast<float*>(buf);
-      if (p.stage_mode == STG_ROWS) {
-        float4* dst = reinterpret_cast<float4*>(rawW + row * D);
-#pragma unroll
-        for (int c = 0; c < D / 4; ++c) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-      } else {
-        const int T = (int)p.z.T;
-        const long long n = n0 + row;
-        const long long b = n / T; const int t = (int)(n - b * T);
-        float* dst = rawW + (b - n0 / T) * (D * T) + t;
-#pragma unroll
-        for (int k = 0; k < D; ++k) dst[k * T] = v[k];
-      }
-    }
-    fence_proxy_async();
-    converter_sync();
-    if (lead && rows > 0) {
-      const StagePlan sp = stage_plan(p, n0, rows);
-      bulk_s2g(p.r_out + (sp.src - p.z.p), smem_u32(buf), sp.bytes);
-      bulk_commit();
-      bulk_wait_read<0>();                   // the store has read the buffer: safe to overwrite it
-    }
-    converter_sync();
-  }
   // per-row power-of-two scale: the largest |component| lands in [2^10, 2^11) (fp16 keeps 11 bits of every
   // component down to 2^-24 of the row maximum); |x|^2 in exact fp32 for the error bound
   float m = 0.f, xx = 0.f;
@@ -559,9 +555,10 @@ vq_assign_f16_kernel(const Params p) {
         unsigned char* buf = sBuf + (size_t)(rt * 2 + pp) * BUF_BYTES;
         int kp = 0;                                 // previous stage's code of this row, fetched before the wait
         if (fuse && row < rows) kp = min(max(__ldg(p.prev_idx + n0 + row), 0), p.prev_K - 1);
-        if (staged && rows > 0) mbar_wait(smem_u32(rawfull + rt * 2 + pp), u & 1, p.err, 8);
-        else mbar_wait(smem_u32(aempty + rt * 2 + pp), (u & 1) ^ 1, p.err, 5);     // nobody fills it for us: wait until free
-        convert_tile(p, buf, n0, rows, row, kp, warp == 10 && lane == 0);
+        convert_tile(p, buf, n0, rows, row, kp, [&]() {
+          if (staged && rows > 0) mbar_wait(smem_u32(rawfull + rt * 2 + pp), u & 1, p.err, 8);
+          else mbar_wait(smem_u32(aempty + rt * 2 + pp), (u & 1) ^ 1, p.err, 5);   // nobody fills it for us: wait until free
+        });
         if (lane == 0) mbar_arrive(smem_u32(afull + rt * 2 + pp));
       }
     }
@@ -725,10 +722,11 @@ vq_assign_f16_res_kernel(const Params p) {
       int kp = 0;
       if (fuse && row < rows) kp = min(max(__ldg(p.prev_idx + n0 + row), 0), p.prev_K - 1);
       const long long c0 = stamps ? clock64() : 0;
-      if (staged) mbar_wait(smem_u32(rawfull + b), u & 1, p.err, 8);
-      else if (u > 0) mbar_wait(smem_u32(aempty + b), (u - 1) & 1, p.err, 5);      // nobody fills it for us: wait until free
-      const long long c1 = stamps ? clock64() : 0;
-      convert_tile(p, buf, n0, rows, row, kp, warp == 10 && lane == 0);
+      convert_tile(p, buf, n0, rows, row, kp, [&]() {
+        if (staged) mbar_wait(smem_u32(rawfull + b), u & 1, p.err, 8);
+        else if (u > 0) mbar_wait(smem_u32(aempty + b), (u - 1) & 1, p.err, 5);    // nobody fills it for us: wait until free
+      });
+      const long long c1 = c0;
       if (lane == 0) mbar_arrive(smem_u32(afull + b));
       if (stamps && warp == 10 && lane == 0 && r < 256) {
         long long* e = stamps + 3 * 1024 * 4 + r * 4;
