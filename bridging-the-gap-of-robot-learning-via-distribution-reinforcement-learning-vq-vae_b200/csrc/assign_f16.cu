@@ -12,18 +12,26 @@
 //     bits of that maximum and keeps the best two packed group maxima of the code tile (1.375 ALU ops
 //     per score in total; the previous split-bf16 kernel needed 3 MMA passes and 3.5).  Per row the
 //     tile results are merged into the best two groups plus the value of the third best.
-//   * proof: with e = rigorous bound on the error of one filter score (fp16 rounding of both operands,
-//     fp32 accumulation, FFMA rounding, id packing), a row whose best group leads the runner-up group by
-//     more than 2e (+ the reference's own fp32 rounding) provably has its arg min inside the best group
-//     (case A); if only the third best trails by that much, inside the best two groups (case B);
-//     otherwise the row goes to the exact kernel through the work list (case C).  Codes whose norm
-//     exceeds 3|x| + 2 min_k|E_k| can never win for a row (neither exactly nor in the filter), so the
-//     bound uses min(max_k|E_k|, 3|x| + 2 min_k|E_k|): dead codes of size 1e5 (the reference's EMA
-//     init, models/vqvae.py:24-26) do not blow it up.
-//   * re-rank (vq_rerank_kernel, a second bandwidth-class launch): the 4 / 8 / 12 candidate codes are evaluated
-//     in exact fp32 with the arithmetic of the CUDA-core kernel (assign_simt.cu): sequential fmaf chains,
-//     d = (|x|^2 + |E|^2) - 2 x.E, ties to the lowest index -- so the result is bit-identical to the exact path.
-//     (An in-kernel re-rank by the converter warps was measured first: correct, but 128 threads cannot keep
+//   * proof: e = rigorous bound on the error of one filter score (fp16 rounding of both operands, fp32
+//     accumulation, FFMA rounding, id packing); thr = 2e + the reference's own fp32 rounding of (A + B) - 2M.
+//     Every code tile reports its best group (value + id) and the value of its second best group, which bounds all
+//     the others of that tile.  Per row (RowTrack) the tiles' best groups are kept as a sorted list g1..g4 (ids for
+//     three) and the two largest "rest of a tile" bounds L, L2 (jL = tile of L).  With theta = g1 - thr
+//     (row_decide): rest of every tile <= theta -> the arg min is provably inside the first k = 1..3 list groups
+//     (kind k, needs g_{k+1} <= theta); only tile jL has a rest above theta -> inside tile jL or list groups 1..3
+//     (kind 4, "wide"); anything else -> exact kernel through the work list (kind 0, 0.014 % of the rows at cfg3).
+//     Codes whose norm exceeds 3|x| + 2 min_k|E_k| can never win for a row (neither exactly nor in the filter), so
+//     the bound uses min(max_k|E_k|, 3|x| + 2 min_k|E_k|): dead codes of size 1e5 (the reference's EMA init,
+//     models/vqvae.py:24-26) do not blow it up.
+//   * finish, all in exact fp32 with the arithmetic of the CUDA-core kernel (assign_simt.cu: sequential fmaf chains,
+//     d = (|x|^2 + |E|^2) - 2 x.E, ties to the lowest index -- bit-identical to the exact path):
+//       - resident kernel: a kind-1 row is first resolved inside the filter kernel with its own fp16 operands
+//         (resolve_group: packed-fp16 products, the best of the 4 codes must lead by thr + 4e-3 |x| R); 93 % of the
+//         rows are final there and never touched again.  The rest go to a compact list;
+//       - vq_rerank_finish_kernel: 4 lanes per listed row evaluate its 4 / 8 / 12 candidate codes from the
+//         group-interleaved fp32 copy of the codebook (codebook.cuh, E4); one warp per wide row scans its code tile;
+//       - streaming kernel (K > 1024): vq_rerank_kernel re-ranks every row (tiles of whole samples staged in smem).
+//     (An in-kernel exact re-rank by the converter warps was measured first: correct, but 128 threads cannot keep
 //     1.25 KB of L2 gathers per row in flight -- 7.7 ms instead of 2 ms per 10 M x 1024 launch.)
 //
 // Two kernels share the converter / epilogue code:
@@ -34,7 +42,9 @@
 //     KiB top out at ~16.5 B/clk/SM (4.6 TB/s chip-wide): 1050 of the 2150 cycles per code-tile pair were that stream
 //     (knock-outs: no MMA, no TMEM load, no math still took 1050; tcgen05.ld itself sustains ~800 B/clk/SM).
 //   * vq_assign_f16_kernel (any K): codebook tiles streamed through a 4-stage ring, two row tiles share every tile.
-// Structure of both (one persistent CTA per SM, 448 threads, every hand-off through mbarriers):
+// Structure of both (one persistent CTA per SM, 448 / 480 threads, every hand-off through mbarriers; the resident kernel
+// has a second MMA-issuing thread (warp 14): one thread needed ~1100 cycles per 128 x 128 unit, more than the tensor
+// core):
 //   warp 0       bulk-TMA producer: (a) prefetches the NEXT tile's raw fp32 rows (one contiguous slab
 //                per 128-row group) into a ping-pong buffer, (b) streams 16 KiB fp16 codebook tiles
 //                (pre-swizzled image written by ema_finalize / codebook_prepare) plus their 528 B of
@@ -918,17 +928,16 @@ __device__ __forceinline__ float row_sq(const float4* xs) {
 // List mode (resident kernel): only the rows the filter could not finish itself; 4 lanes per listed row, the row staged
 // in shared memory by its 4 lanes (16 components each).
 constexpr int RL_LD = D + 4;
-__global__ void __launch_bounds__(256)
-vq_rerank_list_kernel(ZView z, const float4* __restrict__ E4, const float* __restrict__ ee, int K,
-                      int32_t* __restrict__ idx, const int32_t* __restrict__ cand2, const int32_t* __restrict__ cand3,
-                      const int32_t* __restrict__ rr_list, const int32_t* __restrict__ rr_count) {
-  __shared__ __align__(16) float X[64 * RL_LD];
+__device__ __forceinline__ void rerank_list_body(float* X, int bid, int nblocks, const ZView& z, const float4* __restrict__ E4,
+                                                 const float* __restrict__ ee, int K, int32_t* __restrict__ idx,
+                                                 const int32_t* __restrict__ cand2, const int32_t* __restrict__ cand3,
+                                                 const int32_t* __restrict__ rr_list, const int32_t* __restrict__ rr_count) {
   const int c = threadIdx.x & 3, slot = threadIdx.x >> 2;
   const int total = *rr_count;
-  const int per_pass = gridDim.x * 64;
+  const int per_pass = nblocks * 64;
   float* xrow = X + slot * RL_LD;
   for (int base = 0; base < total; base += per_pass) {            // warp-uniform trip count (shuffles below)
-    const int e = base + blockIdx.x * 64 + slot;
+    const int e = base + bid * 64 + slot;
     const bool live = e < total;
     const long long n = live ? rr_list[e] : 0;
     const uint32_t first = live ? (uint32_t)idx[n] : 0u;
@@ -964,13 +973,12 @@ vq_rerank_list_kernel(ZView z, const float4* __restrict__ E4, const float* __res
 
 // Wide rows: one warp per row (staged in shared memory); 4 passes of 8 groups x 4 codes over the 32 groups of the row's
 // code tile, a fifth pass over the row's candidate groups 1..3 (duplicates are harmless), then the warp merges.
-__global__ void __launch_bounds__(256)
-vq_rerank_wide_kernel(ZView z, const float4* __restrict__ E4, const float* __restrict__ ee, int K,
-                      int32_t* __restrict__ idx, const int32_t* __restrict__ cand2, const int32_t* __restrict__ cand3,
-                      const int2* __restrict__ wide, const int32_t* __restrict__ wide_count, int wide_cap) {
-  __shared__ __align__(16) float X[8 * D];
+__device__ __forceinline__ void rerank_wide_body(float* X, int bid, int nblocks, const ZView& z, const float4* __restrict__ E4,
+                                                 const float* __restrict__ ee, int K, int32_t* __restrict__ idx,
+                                                 const int32_t* __restrict__ cand2, const int32_t* __restrict__ cand3,
+                                                 const int2* __restrict__ wide, const int32_t* __restrict__ wide_count, int wide_cap) {
   const int lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int warp = (bid * (int)blockDim.x + (int)threadIdx.x) >> 5, nwarps = (nblocks * (int)blockDim.x) >> 5;
   float* xrow = X + (threadIdx.x >> 5) * D;
   const int total = min(*wide_count, wide_cap);
   for (int w = warp; w < total; w += nwarps) {
@@ -1003,6 +1011,27 @@ vq_rerank_wide_kernel(ZView z, const float4* __restrict__ E4, const float* __res
       if (cand_better(od, oi, best, bidx)) { best = od; bidx = oi; }
     }
     if (lane == 0) idx[n] = bidx;
+  }
+}
+
+// One launch for both: `lblocks` CTAs (the even ones) work on the re-rank list (bound by the 32-byte sectors of the scattered
+// row reads), the others on the wide rows (bound by L1 / L2 reads of the code tile) -- disjoint rows, different
+// bottlenecks, so they overlap instead of queueing (0.24 + 0.28 ms per 10 M x 1024 as two launches).  lblocks == 0:
+// no list (streaming filter, its re-rank is vq_rerank_kernel).
+__global__ void __launch_bounds__(256)
+vq_rerank_finish_kernel(ZView z, const float4* __restrict__ E4, const float* __restrict__ ee, int K,
+                        int32_t* __restrict__ idx, const int32_t* __restrict__ cand2, const int32_t* __restrict__ cand3,
+                        const int32_t* __restrict__ rr_list, const int32_t* __restrict__ rr_count, int lblocks,
+                        const int2* __restrict__ wide, const int32_t* __restrict__ wide_count, int wide_cap) {
+  __shared__ __align__(16) float X[64 * RL_LD];
+  const int bid = (int)blockIdx.x;
+  if (lblocks == 0) {
+    rerank_wide_body(X, bid, (int)gridDim.x, z, E4, ee, K, idx, cand2, cand3, wide, wide_count, wide_cap);
+  } else if (2 * lblocks == (int)gridDim.x) {       // both kinds, interleaved so that they are resident together
+    if (bid & 1) rerank_wide_body(X, bid >> 1, lblocks, z, E4, ee, K, idx, cand2, cand3, wide, wide_count, wide_cap);
+    else rerank_list_body(X, bid >> 1, lblocks, z, E4, ee, K, idx, cand2, cand3, rr_list, rr_count);
+  } else {                                          // list only
+    rerank_list_body(X, bid, lblocks, z, E4, ee, K, idx, cand2, cand3, rr_list, rr_count);
   }
 }
 
@@ -1117,10 +1146,10 @@ int launch_assign_f16(const ZView& z, const float* E, const float* ee, const voi
   // exact re-rank of the 4 / 8 / 12 candidates of every proven row that is not final yet
   {
     const float4* E4 = reinterpret_cast<const float4*>(img + img_e4_offset(K, D));
+    int lblocks = 0;
+    const bool with_wide = !(p.dbg & 16);
     if (p.rr_list) {
-      const int lgrid = (int)max(1LL, min((z.N + 63) / 64, (long long)sm_count() * 8));
-      vq_rerank_list_kernel<<<lgrid, 256, 0, stream>>>(zq, E4, ee, K, idx, p.cand2, p.cand3, p.rr_list, p.rr_count);
-      VQ_LAUNCH_CHECK("vq_rerank_list_kernel");
+      lblocks = (int)max(1LL, min((z.N + 63) / 64, (long long)sm_count() * 8));
     } else {
       // contiguous layouts with T <= 64: tiles of whole samples staged in shared memory
       const bool tiled = p.stage_mode != STG_DIRECT && z.T <= RR_ROWS && (z.mode == Z_BCT || z.T == 1);
@@ -1131,10 +1160,27 @@ int launch_assign_f16(const ZView& z, const float* E, const float* ee, const voi
       else vq_rerank_kernel<false><<<rgrid, RR_THREADS, 0, stream>>>(zq, rpt, E4, ee, K, idx, p.cand2, p.cand3);
       VQ_LAUNCH_CHECK("vq_rerank_kernel");
     }
-    const int wgrid = (int)max(1LL, min((long long)(p.wide_cap + 7) / 8, (long long)sm_count() * 8));
-    if (!(p.dbg & 16))
-    vq_rerank_wide_kernel<<<wgrid, 256, 0, stream>>>(zq, E4, ee, K, idx, p.cand2, p.cand3, p.wide, p.wide_count, p.wide_cap);
-    VQ_LAUNCH_CHECK("vq_rerank_wide_kernel");
+    // launch-bound sizes: one launch for both kinds (interleaved CTAs, -18 us per cfg1 step); at bandwidth-bound sizes
+    // two launches of full width are faster (3.79 vs 3.90 ms per 10 M x 1024 assignment on the same GPU)
+    const bool merged = lblocks > 0 && with_wide && z.N <= F16_SPLIT_MAX_ROWS;
+    const int wfull = (int)max(1LL, min((long long)(p.wide_cap + 7) / 8, (long long)sm_count() * 8));
+    if (merged) {
+      const int half = (int)max(1LL, min((z.N + 63) / 64, (long long)sm_count() * 4));
+      vq_rerank_finish_kernel<<<2 * half, 256, 0, stream>>>(zq, E4, ee, K, idx, p.cand2, p.cand3, p.rr_list, p.rr_count,
+                                                            half, p.wide, p.wide_count, p.wide_cap);
+      VQ_LAUNCH_CHECK("vq_rerank_finish_kernel");
+    } else {
+      if (lblocks > 0) {
+        vq_rerank_finish_kernel<<<lblocks, 256, 0, stream>>>(zq, E4, ee, K, idx, p.cand2, p.cand3, p.rr_list, p.rr_count,
+                                                             lblocks, p.wide, p.wide_count, p.wide_cap);
+        VQ_LAUNCH_CHECK("vq_rerank_finish_kernel(list)");
+      }
+      if (with_wide) {
+        vq_rerank_finish_kernel<<<wfull, 256, 0, stream>>>(zq, E4, ee, K, idx, p.cand2, p.cand3, p.rr_list, p.rr_count,
+                                                           0, p.wide, p.wide_count, p.wide_cap);
+        VQ_LAUNCH_CHECK("vq_rerank_finish_kernel(wide)");
+      }
+    }
   }
   // exact re-do of the rows the filter could not prove (count lives on the device; no host sync)
   unsigned long long* keys = (z.N <= F16_SPLIT_MAX_ROWS)
