@@ -5,7 +5,7 @@ os.environ["VQB200_TC_DEBUG"] = os.environ.get("VQB200_TC_DEBUG", "520")
 import torch, vqb200
 from vqb200 import _lib
 dev = torch.device("cuda:0")
-B, T, K = 1000000, 10, 1024
+B, T, K = 1000000, 10, int(os.environ.get("STAMP_K", "1024"))
 torch.manual_seed(0)
 W = 0.3 * torch.randn(K, 64, device=dev)
 z = 0.5 * torch.randn(B, 64, T, device=dev)
