@@ -95,8 +95,10 @@ def load(build_if_missing=True):
     if _LIB is not None:
         return _LIB
     path = os.environ.get("VQB200_LIB_PATH") or _build.LIB      # development: A/B builds of the same sources
-    if build_if_missing and (not os.path.exists(path) or (os.environ.get("VQB200_REBUILD") == "1")):
-        _build.build()
+    own = path == _build.LIB
+    if build_if_missing and own and (not os.path.exists(path) or os.environ.get("VQB200_REBUILD") == "1"
+                                     or (_build.have_nvcc() and _build.needs_build())):
+        _build.build_locked(force=os.environ.get("VQB200_REBUILD") == "1")
     if not os.path.exists(path):
         raise RuntimeError(f"vqb200: CUDA library {path} is missing and could not be built; "
                            "there is no CPU fallback (run `python __graft_entry__.py build`)")

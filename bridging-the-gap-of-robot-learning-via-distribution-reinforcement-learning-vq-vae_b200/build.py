@@ -20,12 +20,49 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+def have_nvcc():
+    try:
+        _nvcc()
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "vqb200.h"), __file__]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    except RuntimeError:
+        return False
+
+
+def build_locked(force=False):
+    """build() under an exclusive file lock: under torchrun every rank may find the library missing or stale at once."""
+    import fcntl
+    os.makedirs(LIB_DIR, exist_ok=True)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return build(force=force)            # whoever comes second finds an up-to-date library and returns at once
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+STAMP = os.path.join(LIB_DIR, "sources.sha256")
+
+
+def source_hash():
+    """Content hash of everything the library is built from (mtimes do not survive a copy of the tree)."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    deps += [os.path.join(HERE, "..", "include", "vqb200.h"), os.path.abspath(__file__)]
+    for d in deps:
+        if os.path.exists(d):
+            h.update(os.path.basename(d).encode())
+            with open(d, "rb") as f:
+                h.update(f.read())
+    h.update(os.environ.get("VQB200_NVCC_EXTRA", "").encode())
+    return h.hexdigest()
+
+
+def needs_build():
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
+        return True
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -54,10 +91,14 @@ def build(force=False, verbose=False):
         if verbose and out.strip():
             print(out)
         objs.append(o)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [nvcc, "-shared", "-o", tmp] + objs + ["-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp, LIB)                         # readers never see a partial library
+    with open(STAMP, "w") as f:
+        f.write(source_hash())
     return LIB
 
 

@@ -200,6 +200,7 @@ def _close_peer() -> None:
 def disable() -> None:
     global _GROUP, _ENABLED, _PEER_STATUS, _UNIFORM
     _AGREED.clear()
+    _GRAD_SETS.clear()
     _close_peer()
     _GROUP, _ENABLED, _PEER_STATUS, _UNIFORM = None, False, "off", False
 
@@ -209,6 +210,7 @@ def uniform_shards() -> bool:
 
 
 _AGREED = {}
+_GRAD_SETS: dict = {}       # parameter list -> (this rank's grad mask, union over ranks); see average_gradients
 
 
 def agree(key, local: bool) -> bool:
@@ -271,14 +273,43 @@ def shard_bounds(n: int, rank_: Optional[int] = None, world: Optional[int] = Non
     return lo, lo + base + (1 if r < rem else 0)
 
 
+def reset_gradient_sets() -> None:
+    """Forget the agreed gradient sets (collective in effect: the next average_gradients call of every rank re-agrees)."""
+    _GRAD_SETS.clear()
+
+
 def average_gradients(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20) -> int:
-    """DDP-style gradient averaging over the group for parameters that have a gradient.
+    """DDP-style gradient averaging over the group for all parameters that require a gradient.
     Flattens into buckets sized for launch latency (NVSwitch gives full bandwidth to every peer, so
     bucket count -- not link count -- is what matters).  Returns the number of all-reduce calls."""
     if not enabled():
         return 0
     w = float(world_size())
-    grads: List[torch.Tensor] = [p.grad for p in params if p is not None and p.grad is not None]
+    # Which parameters take part is agreed on ONCE per parameter list (a rank whose branch produced no gradient for a
+    # parameter that other ranks have one for contributes zeros and receives the average; parameters without a gradient
+    # on every rank -- EMA codebooks -- stay None as in the reference): bucket sizes and order are then identical on all
+    # ranks.  A gradient that shows up later for a parameter outside the agreed set is an error, not a silent omission.
+    plist = [p for p in params if p is not None and p.requires_grad]
+    local = tuple(1 if p.grad is not None else 0 for p in plist)
+    key = tuple(id(p) for p in plist)
+    known = _GRAD_SETS.get(key)
+    if known is None:
+        dev = next((p.grad.device for p in plist if p.grad is not None), plist[0].device if plist else torch.device("cpu"))
+        m = torch.tensor(local, dtype=torch.int32, device=dev)
+        if m.numel():
+            torch_dist.all_reduce(m, op=torch_dist.ReduceOp.MAX, group=_GROUP)
+        known = (local, tuple(int(v) for v in m.tolist()))
+        _GRAD_SETS[key] = known
+    elif any(has and not take for has, take in zip(local, known[1])):
+        raise RuntimeError("vqb200.dist.average_gradients: a parameter that had no gradient on any rank when the set was "
+                           "agreed has one now on this rank (call vqb200.dist.reset_gradient_sets() on all ranks)")
+    grads: List[torch.Tensor] = []
+    for p, take in zip(plist, known[1]):
+        if not take:
+            continue
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+        grads.append(p.grad)
     calls = 0
     bucket: List[torch.Tensor] = []
     size = 0

@@ -300,6 +300,10 @@ class _RVQFn(torch.autograd.Function):
         ctx.S = S
         ctx.shape = (B, C, T)
         if cfg.use_ema:
+            # the kernels update E_0 through raw pointers (autograd's version counter does not see it): backward must not
+            # read a codebook that a later training forward has moved on, so it always gets its own copy
+            if e0_snapshot is None and ctx.needs_input_grad[0]:
+                e0_snapshot = weights[0].detach().clone()
             ctx.save_for_backward(z, idx, e0_snapshot if e0_snapshot is not None else weights[0].detach())
         else:
             ctx.save_for_backward(z, idx, *residuals[1:], *weights)
@@ -381,7 +385,8 @@ _UNIQ_WS = {}
 
 
 def _unique_workspace(device: torch.device) -> torch.Tensor:
-    key = (device.type, device.index)
+    # one per (device, stream): calls on different streams must not share the bitmap / ticket / entropy words
+    key = (device.type, device.index, int(torch.cuda.current_stream(device).cuda_stream))
     ws = _UNIQ_WS.get(key)
     if ws is None:
         ws = torch.empty(int(_lib.load().vqb200_unique_workspace_bytes()), dtype=torch.uint8, device=device)

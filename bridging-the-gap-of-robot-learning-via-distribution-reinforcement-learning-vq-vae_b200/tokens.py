@@ -145,6 +145,8 @@ def decode(module, tok: TokenBatch) -> torch.Tensor:
     """Tokens -> quantized latent [B,C,T] (what `module(z)[1]` returned at encode time), ready for the decoder."""
     lib = _lib.load()
     sp = tok.spec
+    _validate_spec(sp, "vqb200.tokens.decode")
+    _check_module(module, sp)
     codes, digits = unpack(tok)
     dev = tok.data.device
     out = torch.empty((sp.B, sp.C, sp.T), dtype=torch.float32, device=dev)
@@ -177,6 +179,39 @@ def decode(module, tok: TokenBatch) -> torch.Tensor:
     return out
 
 
+def _validate_spec(sp: TokenSpec, where: str) -> None:
+    """A token header is untrusted input: the device kernels index with these fields."""
+    ints = (sp.B, sp.C, sp.T, sp.S, sp.code_bits, sp.d, sp.digit_bits, sp.bytes_per_token)
+    if any((not isinstance(v, int)) or v < 0 for v in ints) or sp.method not in ("vq", "rvq", "fsq", "lfq", "hybrid"):
+        raise RuntimeError(f"{where}: malformed token header")
+    if sp.code_bits > 31 or sp.digit_bits > 32 or sp.S > 64 or sp.d > 64:
+        raise RuntimeError(f"{where}: token header out of range (code_bits={sp.code_bits}, digit_bits={sp.digit_bits}, S={sp.S}, d={sp.d})")
+    want = (sp.S * sp.code_bits + sp.d * sp.digit_bits + 7) // 8
+    if sp.bytes_per_token != want:
+        raise RuntimeError(f"{where}: header says {sp.bytes_per_token} bytes per token, its layout needs {want}")
+
+
+def _check_module(module, sp: TokenSpec) -> None:
+    """The tokens must belong to a module of this shape before any kernel indexes its weights with them."""
+    if sp.method == "hybrid":
+        dims, d = [l.embedding_dim for l in module.vq.layers], module.fsq.fsq_dim
+        po = module.fsq.project_out.weight
+    elif sp.method == "rvq":
+        dims, d, po = [l.embedding_dim for l in module.layers], 0, None
+    elif sp.method == "vq":
+        dims, d, po = [module.embedding_dim], 0, None
+    elif sp.method == "fsq":
+        dims, d, po = [], module.fsq_dim, module.project_out.weight
+    else:
+        return
+    if any(c != sp.C for c in dims):
+        raise RuntimeError(f"vqb200.tokens.decode: tokens are for C={sp.C}, module has embedding_dim {dims}")
+    if d != sp.d:
+        raise RuntimeError(f"vqb200.tokens.decode: tokens carry {sp.d} FSQ digits, module has {d}")
+    if po is not None and (po.shape[0] != sp.C or po.shape[1] != sp.d):
+        raise RuntimeError(f"vqb200.tokens.decode: project_out is {tuple(po.shape)}, tokens need ({sp.C}, {sp.d}, 1)")
+
+
 # ---- file format: MAGIC | u32 header length | JSON header (TokenSpec) | payload (B*T*bytes_per_token bytes) --------
 def save(path: str, tok: TokenBatch) -> None:
     if tok.saturated is not None and int(tok.saturated.item()) != 0:
@@ -196,6 +231,7 @@ def load(path: str, device="cpu") -> TokenBatch:
         (hl,) = struct.unpack("<I", f.read(4))
         spec = TokenSpec(**json.loads(f.read(hl).decode()))
         payload = f.read()
+    _validate_spec(spec, path)
     n = spec.B * spec.T * spec.bytes_per_token
     if len(payload) != n:
         raise RuntimeError(f"{path}: payload has {len(payload)} bytes, header promises {n}")

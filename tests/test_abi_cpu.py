@@ -162,6 +162,31 @@ def test_token_layout_and_file_format_need_no_gpu(tmp_path):
     assert back.spec == hy and torch.equal(back.data, tb.data)
     with pytest.raises(RuntimeError):
         tokens.decode(vqb200.HybridVQ(64, [8, 5, 5, 5], 512), back)      # CPU tokens: no CPU path
+    # a token header is untrusted input: a layout that disagrees with its own fields, or with the module, is rejected
+    # before any kernel could index with it
+    import dataclasses, struct
+    bad = dataclasses.replace(hy, bytes_per_token=hy.bytes_per_token - 1)
+    raw = json.dumps(dataclasses.asdict(bad)).encode()
+    g = str(tmp_path / "bad.vqtok")
+    with open(g, "wb") as fh:
+        fh.write(tokens.MAGIC + struct.pack("<I", len(raw)) + raw + bytes(21 * (hy.bytes_per_token - 1)))
+    with pytest.raises(RuntimeError, match="bytes per token"):
+        tokens.load(g)
+    with pytest.raises(RuntimeError, match="embedding_dim"):
+        tokens.decode(vqb200.HybridVQ(32, [8, 5, 5, 5], 512), back)      # tokens are for C = 64
+    with pytest.raises(RuntimeError, match="FSQ digits"):
+        tokens.decode(vqb200.HybridVQ(64, [8, 5, 5], 512), back)         # 3 digits instead of 4
+
+
+def test_library_staleness_is_detected_by_content(tmp_path, monkeypatch):
+    """_lib.load() rebuilds when the sources changed since the library was linked; the check hashes file contents
+    (mtimes do not survive a copy of the tree to the GPU box)."""
+    from vqb200 import build as b
+    if not os.path.exists(b.LIB):
+        pytest.skip("library not built")
+    assert os.path.exists(b.STAMP) and not b.needs_build()
+    monkeypatch.setenv("VQB200_NVCC_EXTRA", "-DVQB200_SOME_VARIANT=1")    # flags are part of the hash
+    assert b.needs_build()
 
 
 def test_staged_reference_is_unmodified_when_present():

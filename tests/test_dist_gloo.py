@@ -67,6 +67,23 @@ def _worker(rank, world, port, tmp):
     q = torch.nn.Parameter(torch.zeros(3))                      # no grad: skipped
     calls = vqb200.dist.average_gradients([p, q])
     assert calls == 1 and torch.allclose(p.grad, torch.full((5,), (1 + world) / 2))
+    assert q.grad is None                                       # no rank has one: stays None (EMA codebooks)
+    # a parameter that only SOME ranks have a gradient for: the others contribute zeros and receive the average
+    u = torch.nn.Parameter(torch.zeros(4))
+    v = torch.nn.Parameter(torch.zeros(2))
+    v.grad = torch.ones(2)
+    if rank == 0:
+        u.grad = torch.full((4,), 2.0)
+    calls = vqb200.dist.average_gradients([u, v])
+    assert calls == 1 and torch.allclose(u.grad, torch.full((4,), 2.0 / world)) and torch.allclose(v.grad, torch.ones(2))
+    u.grad = None if rank == 1 else u.grad                      # zero_grad(set_to_none=True): same agreed set, still fine
+    assert vqb200.dist.average_gradients([u, v]) == 1
+    q.grad = torch.ones(3)                                      # outside the agreed set of [p, q]: loud, not silently skipped
+    try:
+        vqb200.dist.average_gradients([p, q])
+        raise AssertionError("expected a RuntimeError")
+    except RuntimeError as e:
+        assert "had no gradient on any rank" in str(e)
     open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     dist.destroy_process_group()
 
