@@ -87,3 +87,52 @@ def test_cfg5_k65536_parity():
     rng = np.random.default_rng(1240)
     z = rng.standard_normal((N, D, 1)).astype(np.float32)
     _vq_step(mod, st, z, rng.standard_normal((N, D, 1)).astype(np.float32), 1.0, True)
+
+
+@pytest.mark.parametrize("B,T,K,regime,zmode,perm", [
+    (1, 1, 1024, "small", "plain", False),            # a single row
+    (1, 129, 1024, "small", "plain", True),           # one row more than a row tile
+    (13, 3, 777, "small", "plain", False),            # ragged everything
+    (4099, 10, 1030, "small", "plain", False),        # streaming kernel, 6 codes in the last code tile
+    (20000, 1, 1025, "small", "plain", True),
+    (40960, 10, 1024, "small", "rowscales", False),   # every row at its own magnitude, 1e-18 .. 1e18
+    (40960, 10, 2048, "small", "rowscales", False),
+    (40960, 10, 1024, "normal", "huge", False),       # 1e17-sized data and codes
+    (40960, 10, 1024, "small", "zeros", False),       # exactly-zero rows and components
+    (40960, 10, 1024, "small", "nonfinite", False),   # NaN / Inf rows, one NaN code
+    (40960, 10, 2048, "small", "nonfinite", False),
+    (40960, 1, 1024, "dead", "rowscales", True),      # a few live codes among 3e4-times larger dead ones
+    (100000, 10, 1024, "dup", "rowscales", False),    # duplicated codes: ties everywhere
+])
+def test_tensor_core_assignment_equals_exact_kernel_on_edge_regimes(B, T, K, regime, zmode, perm):
+    """The tcgen05 filter + exact finish must give the SAME indices as the exact CUDA-core kernel (which the other
+    tests hold to the oracle), bit for bit, whatever the data looks like: the filter may only ever hand rows over."""
+    import vqb200
+    from vqb200 import _lib
+    dev = torch.device("cuda:0")
+    D = 64
+    torch.manual_seed(0)
+    W = torch.randn(K, D, device=dev)
+    if regime == "small":
+        W *= 0.3
+    elif regime == "dup":
+        W[K // 2:] = W[: K - K // 2]
+    elif regime == "dead":
+        W[::3] *= 3e4
+    z = (0.5 * torch.randn(B, T, D, device=dev)).permute(0, 2, 1) if perm else 0.5 * torch.randn(B, D, T, device=dev)
+    if zmode == "rowscales":
+        z = z * (10.0 ** (36 * torch.rand(B, 1, T, device=dev) - 18))
+    elif zmode == "huge":
+        z, W = z * 1e17, W * 1e17
+    elif zmode == "zeros":
+        z = z * (torch.rand(B, 1, T, device=dev) > 0.33) * (torch.rand_like(z) > 0.2)
+    elif zmode == "nonfinite":
+        z = z.clone()
+        z.view(-1)[::977] = float("nan"); z.view(-1)[5::1999] = float("inf"); z.view(-1)[11::2999] = float("-inf")
+        W = W.clone(); W[K // 3, 7] = float("nan")
+    st = vqb200.QuantizerState(K, D, dev)
+    i_exact = vqb200.vq_assign(z, W, st, _lib.ASSIGN_SIMT)
+    i_tc = vqb200.vq_assign(z, W, st, _lib.ASSIGN_TC)
+    torch.cuda.synchronize()
+    assert int(st._assign_ws[:8].view(torch.int32)[1]) == 0          # error word of the kernel
+    assert torch.equal(i_exact, i_tc)

@@ -21,7 +21,7 @@ def timeit(fn, reps=5, warm=2):
     return a.elapsed_time(b) / reps
 
 
-def case(B, T, K, regime="small", seed=0, time_it=False, perm=False, D=64):
+def case(B, T, K, regime="small", seed=0, time_it=False, perm=False, D=64, zmode="plain"):
     torch.manual_seed(seed)
     W = torch.randn(K, D, device=dev)
     if regime == "small":
@@ -41,6 +41,16 @@ def case(B, T, K, regime="small", seed=0, time_it=False, perm=False, D=64):
         z = (0.5 * torch.randn(B, T, D, device=dev)).permute(0, 2, 1)
     else:
         z = 0.5 * torch.randn(B, D, T, device=dev)
+    if zmode == "rowscales":             # every row at its own magnitude, 1e-18 .. 1e18
+        z = z * (10.0 ** (36 * torch.rand(B, 1, T, device=dev) - 18))
+    elif zmode == "huge":
+        z = z * 1e17; W = W * 1e17
+    elif zmode == "zeros":               # a third of the rows exactly zero, some components exactly zero
+        z = z * (torch.rand(B, 1, T, device=dev) > 0.33) * (torch.rand_like(z) > 0.2)
+    elif zmode == "nonfinite":           # NaN / Inf rows and one NaN code: both paths must agree (NaN wins, first index)
+        z = z.clone()
+        z.view(-1)[::977] = float("nan"); z.view(-1)[5::1999] = float("inf"); z.view(-1)[11::2999] = float("-inf")
+        W = W.clone(); W[K // 3, 7] = float("nan")
     i_simt = vqb200.vq_assign(z, W, st, _lib.ASSIGN_SIMT)
     i_tc = vqb200.vq_assign(z, W, st, _lib.ASSIGN_TC)
     torch.cuda.synchronize()
@@ -48,7 +58,7 @@ def case(B, T, K, regime="small", seed=0, time_it=False, perm=False, D=64):
     ws = st._assign_ws[off:off + 256].view(torch.int32)
     flagged, err, two, wide, rr = int(ws[0]), int(ws[1]), int(ws[2]) + int(ws[3]), int(ws[4]), int(ws[5])
     mism = int((i_simt != i_tc).sum())
-    out = dict(B=B, T=T, K=K, D=D, regime=regime, perm=perm, N=B * T, mismatches=mism, flagged=flagged,
+    out = dict(B=B, T=T, K=K, D=D, regime=regime, zmode=zmode, perm=perm, N=B * T, mismatches=mism, flagged=flagged,
                multi_groups=two, wide=wide, rerank_list=rr, err=err)
     if mism:
         bad = (i_simt != i_tc).reshape(-1).nonzero().reshape(-1)[:5]
@@ -66,7 +76,30 @@ def case(B, T, K, regime="small", seed=0, time_it=False, perm=False, D=64):
     return mism
 
 
+def edge_cases():
+    total = 0
+    total += case(1, 1, 1024)                          # a single row
+    total += case(1, 129, 1024, perm=True)             # one row more than a tile
+    total += case(13, 3, 777)                          # ragged everything
+    total += case(4099, 10, 1030)                      # streaming kernel, 6 codes in the last tile
+    total += case(20000, 10, 4099, "normal")
+    total += case(20000, 1, 1025, perm=True)
+    total += case(40960, 10, 1024, zmode="rowscales")
+    total += case(40960, 10, 2048, zmode="rowscales")
+    total += case(40960, 10, 1024, "normal", zmode="huge")
+    total += case(40960, 10, 1024, zmode="zeros")
+    total += case(40960, 10, 4096, zmode="zeros")
+    total += case(40960, 10, 1024, zmode="nonfinite")
+    total += case(40960, 10, 2048, zmode="nonfinite")
+    total += case(40960, 1, 1024, "dead", zmode="rowscales", perm=True)
+    total += case(300000, 10, 1024, "dup", zmode="rowscales")
+    print("TOTAL MISMATCHES (edge)", total)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "edge":
+        edge_cases()
+        sys.exit(0)
     total = 0
     total += case(2, 128, 128)                 # one CTA tile, one code tile
     total += case(1, 256, 256, perm=True)
