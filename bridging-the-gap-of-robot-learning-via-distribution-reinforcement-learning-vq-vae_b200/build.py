@@ -59,8 +59,12 @@ def source_hash():
 
 
 def needs_build():
-    if not os.path.exists(LIB) or not os.path.exists(STAMP):
+    """True when the library is missing or was linked from different sources.  A library WITHOUT a stamp (copied in
+    from elsewhere) is taken as it is: rebuilding on a guess would cost minutes on every rank of a GPU job."""
+    if not os.path.exists(LIB):
         return True
+    if not os.path.exists(STAMP):
+        return False
     with open(STAMP) as f:
         return f.read().strip() != source_hash()
 
