@@ -42,7 +42,7 @@
 //     KiB top out at ~16.5 B/clk/SM (4.6 TB/s chip-wide): 1050 of the 2150 cycles per code-tile pair were that stream
 //     (knock-outs: no MMA, no TMEM load, no math still took 1050; tcgen05.ld itself sustains ~800 B/clk/SM).
 //   * vq_assign_f16_kernel (any K): codebook tiles streamed through a 4-stage ring, two row tiles share every tile.
-// Structure of both (one persistent CTA per SM, 448 / 480 threads, every hand-off through mbarriers; the resident kernel
+// Structure of both (one persistent CTA per SM, 448 / 608 threads, every hand-off through mbarriers; the resident kernel
 // has a second MMA-issuing thread (warp 14): one thread needed ~1100 cycles per 128 x 128 unit, more than the tensor
 // core):
 //   warp 0       bulk-TMA producer: (a) prefetches the NEXT tile's raw fp32 rows (one contiguous slab
@@ -53,7 +53,8 @@
 //   warps 2-9    epilogue: two groups of 4 warps, one 128-row tile each; tcgen05.ld the fp32 accumulators
 //                (one row per thread, software-pipelined) and run the group filter
 //   warps 10-13  converter: turns the prefetched raw rows IN PLACE into the swizzled K-major fp16 A operand
-//                of the next tile (and, for RVQ stages >= 1, applies the residual update on the way)
+//                of the next tile (and, for RVQ stages >= 1, applies the residual update on the way); the resident
+//                kernel has 8 converter warps (10-13, 15-18), two threads per row (convert_tile2)
 //   TMEM: 4 accumulators of 128 columns (2 row tiles x 2 stages) = all 512 columns, so the MMAs of
 //   code tile j+1 overlap the epilogue of code tile j.
 #include <stdlib.h>
@@ -97,7 +98,7 @@ constexpr int RES_MAX_NT = 8;               // resident kernel: at most 8 code t
 constexpr int RES_MAX_BUF = 4;
 enum StageMode : int { STG_DIRECT = 0, STG_ROWS = 1, STG_BCT = 2 };
 constexpr int NTHREADS = 448;
-constexpr int NTHREADS_RES = 480;        // resident kernel: one more warp (second MMA issuer)
+constexpr int NTHREADS_RES = 608;        // resident kernel: + second MMA issuer (warp 14) + 4 more converter warps (15-18)
 // instruction descriptor: D=f32, A=B=f16, both K-major, N=128, M=128
 constexpr uint32_t IDESC_F16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 constexpr int KIND_SHIFT = 28;              // idx[n] = best group | kind << 28 until the re-rank has run
@@ -248,6 +249,111 @@ __device__ __forceinline__ void convert_tile(const Params& p, unsigned char* buf
   *reinterpret_cast<float2*>(buf + A_BYTES + row * 8) = make_float2(inv, xx);
   fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)
   converter_sync();
+}
+
+
+// Resident kernel: the same conversion with TWO threads per row (8 converter warps).  Thread (row, h) owns the 16-byte
+// chunks j = h, h + 2, h + 4, h + 6 of the row's A operand, i.e. dims 8j .. 8j+7: half the registers per thread (no
+// spills with the residual update fused in), the codeword arrives in ONE batch of 8 loads per thread instead of two, and
+// twice as many loads / stores are in flight.  The two partner threads are adjacent lanes (shuffles for max and |x|^2);
+// their shared-memory reads are 80 floats apart in the [B,C,T] layout (bank + 16: no conflict between partners).
+__device__ __forceinline__ void converter_sync2() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <class Wait>
+__device__ __forceinline__ void convert_tile2(const Params& p, unsigned char* buf, long long n0, int rows, int row, int h,
+                                              int kp, Wait wait_for_rows) {
+  const float* raw = reinterpret_cast<const float*>(buf);
+  const bool fuse = p.r_out != nullptr;
+  float v[D / 2];                               // v[8 * i + e] = dim 8 * (h + 2 i) + e
+  const float4* __restrict__ q4 = reinterpret_cast<const float4*>(p.prev_E + (size_t)kp * D);
+  wait_for_rows();
+  if (row < rows) {
+    const long long n = n0 + row;
+    if (p.stage_mode == STG_ROWS) {
+      const float4* src = reinterpret_cast<const float4*>(raw + row * D);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = h + 2 * i;
+        const float4 f0 = src[2 * j], f1 = src[2 * j + 1];
+        v[8 * i + 0] = f0.x; v[8 * i + 1] = f0.y; v[8 * i + 2] = f0.z; v[8 * i + 3] = f0.w;
+        v[8 * i + 4] = f1.x; v[8 * i + 5] = f1.y; v[8 * i + 6] = f1.z; v[8 * i + 7] = f1.w;
+      }
+    } else if (p.stage_mode == STG_BCT) {
+      const int T = (int)p.z.T;
+      const long long b = n / T; const int t = (int)(n - b * T);
+      const float* src = raw + (b - n0 / T) * (D * T) + t;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[8 * i + e] = src[(8 * (h + 2 * i) + e) * T];
+    } else {
+      const float* src = p.z.p + p.z.row_base(n);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[8 * i + e] = __ldg(src + (long long)(8 * (h + 2 * i) + e) * p.z.sC);
+    }
+    if (fuse) {
+      // r = x - (x + (q - x)): the same three roundings as the stand-alone residual kernel; straight to r_out
+      float* __restrict__ dst = p.r_out + ((p.stage_mode == STG_ROWS) ? n * D : (n / p.z.T) * (long long)(D * p.z.T) + (n % p.z.T));
+      const int so = (p.stage_mode == STG_ROWS) ? 1 : (int)p.z.T;
+      float4 q[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { q[2 * i] = __ldg(q4 + 2 * (h + 2 * i)); q[2 * i + 1] = __ldg(q4 + 2 * (h + 2 * i) + 1); }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float qv[8] = {q[2 * i].x, q[2 * i].y, q[2 * i].z, q[2 * i].w, q[2 * i + 1].x, q[2 * i + 1].y, q[2 * i + 1].z, q[2 * i + 1].w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float x = v[8 * i + e];
+          v[8 * i + e] = __fsub_rn(x, __fadd_rn(x, __fsub_rn(qv[e], x)));
+        }
+        const int d0 = 8 * (h + 2 * i);
+        if (p.stage_mode == STG_ROWS) {
+          *reinterpret_cast<float4*>(dst + d0) = make_float4(v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3]);
+          *reinterpret_cast<float4*>(dst + d0 + 4) = make_float4(v[8 * i + 4], v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dst[(d0 + e) * so] = v[8 * i + e];
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < D / 2; ++k) v[k] = 0.f;
+  }
+  converter_sync2();                         // every raw read of this buffer is done
+  float m = 0.f, xx = 0.f;
+#pragma unroll
+  for (int k = 0; k < D / 2; ++k) { m = fmaxf(m, fabsf(v[k])); xx = fmaf(v[k], v[k], xx); }
+  // NaN components: fmaxf drops them, the sum keeps them
+  const bool nan_here = !(xx == xx);
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+  xx += __shfl_xor_sync(0xffffffffu, xx, 1);
+  const bool bad = __shfl_xor_sync(0xffffffffu, (int)nan_here, 1) != 0 || nan_here;
+  float sx = 1.0f, inv = 1.0f;
+  {
+    const int eb = (int)((__float_as_uint(m) >> 23) & 255u);
+    if (m != 0.f) {
+      if (eb < 27 || eb == 255 || !(xx < 3.0e38f)) inv = -1.0f;       // tiny / non-finite row: exact kernel
+      else { sx = __uint_as_float((unsigned)(264 - eb) << 23); inv = __uint_as_float((unsigned)(eb - 10) << 23); }
+    }
+    if (bad || !(m == m) || !(xx == xx)) inv = -1.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = h + 2 * i;
+    uint32_t hw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __half2 hh = __floats2half2_rn(v[8 * i + 2 * e] * sx, v[8 * i + 2 * e + 1] * sx);
+      hw[e] = *reinterpret_cast<const uint32_t*>(&hh);
+    }
+    const int off = row * 128 + ((j ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(buf + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  }
+  if (h == 0) *reinterpret_cast<float2*>(buf + A_BYTES + row * 8) = make_float2(inv, xx);
+  fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)
+  converter_sync2();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -650,7 +756,7 @@ vq_assign_f16_res_kernel(const Params p) {
     for (int i = 0; i < RES_MAX_BUF; ++i) {
       // a row buffer is free again when the tensor core has read its last A operand AND the job's 4 epilogue warps
       // are done with it (they re-read their fp16 row to resolve the winning group at the end of the job)
-      mbar_init(smem_u32(rawfull + i), 1); mbar_init(smem_u32(afull + i), 4); mbar_init(smem_u32(aempty + i), 5);
+      mbar_init(smem_u32(rawfull + i), 1); mbar_init(smem_u32(afull + i), 8); mbar_init(smem_u32(aempty + i), 5);
     }
     fence_barrier_init();
   }
@@ -725,9 +831,10 @@ vq_assign_f16_res_kernel(const Params p) {
         b += 2; if (b >= nbuf) { b -= nbuf; ++u; }
       }
     }
-  } else if (warp >= 10 && warp < 14) {
-    // ================= converter: jobs in order =================
-    const int row = (warp - 10) * 32 + lane;
+  } else if (warp >= 10 && warp != 14) {
+    // ================= converter (8 warps, two threads per row): jobs in order =================
+    const int ct = (warp < 14 ? warp - 10 : warp - 11) * 32 + lane;       // 0 .. 255
+    const int row = ct >> 1, h = ct & 1;
     const bool fuse = p.r_out != nullptr;
     for (int r = 0; r < njobs; ++r) {
       const int b = r % nbuf;
@@ -738,15 +845,14 @@ vq_assign_f16_res_kernel(const Params p) {
       int kp = 0;
       if (fuse && row < rows) kp = min(max(__ldg(p.prev_idx + n0 + row), 0), p.prev_K - 1);
       const long long c0 = stamps ? clock64() : 0;
-      convert_tile(p, buf, n0, rows, row, kp, [&]() {
+      convert_tile2(p, buf, n0, rows, row, h, kp, [&]() {
         if (staged) mbar_wait(smem_u32(rawfull + b), u & 1, p.err, 8);
         else if (u > 0) mbar_wait(smem_u32(aempty + b), (u - 1) & 1, p.err, 5);    // nobody fills it for us: wait until free
       });
-      const long long c1 = c0;
       if (lane == 0) mbar_arrive(smem_u32(afull + b));
       if (stamps && warp == 10 && lane == 0 && r < 256) {
         long long* e = stamps + 3 * 1024 * 4 + r * 4;
-        e[0] = c0; e[1] = c1; e[2] = clock64(); e[3] = r;
+        e[0] = c0; e[1] = c0; e[2] = clock64(); e[3] = r;
       }
     }
   } else {
