@@ -126,6 +126,9 @@ struct Params {
   int2* wide;                     // {row, code tile} of rows whose candidates are a whole code tile + (cand1..3)
   int32_t* wide_count;
   int wide_cap;
+  int wide_buckets;               // resident kernel at bandwidth-bound sizes: one list of wide rows PER CODE TILE (`wide` is then
+                                  // int32 [NT][wide_cap], counts at wide_count[0..NT)), so that the re-rank can keep the tile in
+                                  // shared memory (vq_rerank_wide_tile_kernel)
   int32_t* stat;                  // [0..1] rows with 2 / 3 candidate groups (only counted when dbg & 4)
   int* err;
   // fused residual update (RVQ stages >= 1): the staged rows are r_prev; the converter forms
@@ -476,9 +479,15 @@ __device__ __forceinline__ uint32_t row_decide(const RowTrack& tr, float inv_sx,
 __device__ __forceinline__ void row_emit(const Params& p, const RowTrack& tr, bool valid, uint32_t kind, int final_code,
                                          long long n, int lane) {
   if (valid && kind == KIND_WIDE) {
-    const int pos = atomicAdd(p.wide_count, 1);
-    if (pos < p.wide_cap) p.wide[pos] = make_int2((int)n, tr.jL);
-    else kind = 0;
+    if (p.wide_buckets) {
+      const int pos = atomicAdd(p.wide_count + tr.jL, 1);
+      if (pos < p.wide_cap) reinterpret_cast<int32_t*>(p.wide)[(size_t)tr.jL * p.wide_cap + pos] = (int32_t)n;
+      else kind = 0;
+    } else {
+      const int pos = atomicAdd(p.wide_count, 1);
+      if (pos < p.wide_cap) p.wide[pos] = make_int2((int)n, tr.jL);
+      else kind = 0;
+    }
   }
   if (valid) {
     if (final_code >= 0) {
@@ -1126,6 +1135,71 @@ __device__ __forceinline__ void rerank_wide_body(float* X, int bid, int nblocks,
   }
 }
 
+// Wide rows of the resident filter at bandwidth-bound sizes, bucketed by code tile: a CTA keeps ONE tile of the interleaved
+// fp32 copy (128 codes x 64 dims = 32 KiB, groups padded to 1088 B so that the 8 groups x 4 codes a warp reads per step
+// fall into 8 different 16-byte bank groups) in shared memory and runs its warps over that tile's rows.  The list-based
+// kernel re-read the 32 KiB per row through L1 / L2 (3.5 GB per 10 M x 1024 call, 0.28 ms); same arithmetic, same bits.
+constexpr int WT_LD = 68;                      // float4 per group in shared memory (64 + 4 of padding)
+__global__ void __launch_bounds__(256)
+vq_rerank_wide_tile_kernel(ZView z, const float4* __restrict__ E4, const float* __restrict__ ee, int K, int NT,
+                           int32_t* __restrict__ idx, const int32_t* __restrict__ cand2, const int32_t* __restrict__ cand3,
+                           const int32_t* __restrict__ wide_rows, const int32_t* __restrict__ wide_counts, int wide_cap) {
+  __shared__ __align__(16) float4 sE[32 * WT_LD];
+  __shared__ float s_ee[128];
+  __shared__ __align__(16) float X[8 * D];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
+  const int tile = (int)blockIdx.x % NT, sub = (int)blockIdx.x / NT, nsub = (int)gridDim.x / NT;
+  if (sub >= nsub) return;                                     // grid not a multiple of NT
+  const int count = min(wide_counts[tile], wide_cap);
+  if (sub * 8 >= count) return;
+  for (int i = tid; i < 32 * 64; i += 256) sE[(i >> 6) * WT_LD + (i & 63)] = __ldg(E4 + (size_t)tile * (32 * 64) + i);
+  if (tid < 128) s_ee[tid] = (tile * 128 + tid < K) ? __ldg(ee + tile * 128 + tid) : 0.f;
+  __syncthreads();
+  float* xrow = X + warp * D;
+  const float4* xs = reinterpret_cast<const float4*>(xrow);
+  for (int w = sub * 8 + warp; w < count; w += nsub * 8) {
+    const long long n = wide_rows[(size_t)tile * wide_cap + w];
+    __syncwarp();
+    {
+      const float* src = z.p + z.row_base(n);
+      xrow[lane] = __ldg(src + (long long)lane * z.sC);
+      xrow[lane + 32] = __ldg(src + (long long)(lane + 32) * z.sC);
+    }
+    __syncwarp();
+    const float xx = row_sq(xs);
+    float best = INFINITY; int bidx = INT_MAX;
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) {
+      const int gl = pass * 8 + g;                             // group inside the tile
+      const int code = (tile * 32 + gl) * 4 + c;
+      if (code < K) {
+        const float4* e4 = sE + gl * WT_LD + c;
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < D / 4; ++q) {
+          const float4 e = e4[4 * q];
+          const float4 x = xs[q];
+          acc = fmaf(x.x, e.x, acc); acc = fmaf(x.y, e.y, acc); acc = fmaf(x.z, e.z, acc); acc = fmaf(x.w, e.w, acc);
+        }
+        const float d = __fsub_rn(__fadd_rn(xx, s_ee[gl * 4 + c]), __fmul_rn(2.0f, acc));
+        if (cand_better(d, code, best, bidx)) { best = d; bidx = code; }
+      }
+    }
+    if (g < 3) {
+      const int grp = (g == 0) ? (int)((uint32_t)idx[n] & ((1u << KIND_SHIFT) - 1)) : (g == 1) ? __ldg(cand2 + n) : __ldg(cand3 + n);
+      if (grp * 4 + c < K) exact_code_e4s(xs, xx, E4, ee, grp, c, best, bidx);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (cand_better(od, oi, best, bidx)) { best = od; bidx = oi; }
+    }
+    if (lane == 0) idx[n] = bidx;
+  }
+}
+
 // One launch for both: `lblocks` CTAs (the even ones) work on the re-rank list (bound by the 32-byte sectors of the scattered
 // row reads), the others on the wide rows (bound by L1 / L2 reads of the code tile) -- disjoint rows, different
 // bottlenecks, so they overlap instead of queueing (0.24 + 0.28 ms per 10 M x 1024 as two launches).  lblocks == 0:
@@ -1156,12 +1230,12 @@ bool assign_f16_eligible(const ZView& z, int K, int D) {
 // workspace: 64 int32 header ([0] list_count, [1] error word, [2..3] rows with 2 / 3 candidate groups (debug),
 // [4] wide_count, [5] re-rank list count), then int32 arrays: row list (N), second and third candidate group, re-rank
 // list (N each), wide records
-// (2 * wide_cap); for N <= SPLIT_MAX_ROWS additionally N 64-bit merge keys (8-byte aligned) so that the exact kernel
+// (RES_MAX_NT * wide_cap: one {row, tile} list, or one row list per code tile); for N <= SPLIT_MAX_ROWS additionally N 64-bit merge keys (8-byte aligned) so that the exact kernel
 // can split short work lists over codes
 constexpr long long F16_SPLIT_MAX_ROWS = 262144;
 static long long f16_wide_cap(long long N) { return N / 8 + 64; }
 static size_t f16_n2(long long N) { return ((size_t)(N > 0 ? N : 0) + 1) & ~(size_t)1; }      // per-row arrays keep 8-byte alignment
-static size_t f16_ints(long long N) { return 64 + 4 * f16_n2(N) + 2 * (size_t)f16_wide_cap(N > 0 ? N : 0); }
+static size_t f16_ints(long long N) { return 64 + 4 * f16_n2(N) + (size_t)f16::RES_MAX_NT * (size_t)f16_wide_cap(N > 0 ? N : 0); }
 static size_t f16_keys_offset(long long N) { return (f16_ints(N) * sizeof(int32_t) + 7) & ~(size_t)7; }
 size_t assign_f16_workspace_bytes(long long N) {
   return (N > 0 && N <= F16_SPLIT_MAX_ROWS) ? f16_keys_offset(N) + (size_t)N * sizeof(unsigned long long)
@@ -1204,6 +1278,7 @@ int launch_assign_f16(const ZView& z, const float* E, const float* ee, const voi
   p.wide = reinterpret_cast<int2*>(wsi + 64 + 4 * f16_n2(z.N));
   p.wide_cap = (int)f16_wide_cap(z.N);
   p.wide_count = wsi + 4;
+  p.wide_buckets = 0;
   p.list_count = wsi;
   p.err = wsi + 1;
   p.stat = wsi + 2;
@@ -1238,6 +1313,7 @@ int launch_assign_f16(const ZView& z, const float* E, const float* ee, const voi
     }
     p.ntiles = (z.N + p.R - 1) / p.R;
     p.rr_list = wsi + 64 + 3 * f16_n2(z.N);          // the kernel finishes most rows itself and lists the rest
+    if (z.N > F16_SPLIT_MAX_ROWS && !(p.dbg & 16384)) { p.wide_buckets = 1; p.wide_count = wsi + 8; }
     const int grid = (int)max(1LL, min((p.ntiles + 1) / 2, (long long)sm_count()));
     vq_assign_f16_res_kernel<<<grid, NTHREADS_RES, smem, stream>>>(p);
     VQ_LAUNCH_CHECK("vq_assign_f16_res_kernel");
@@ -1287,7 +1363,12 @@ int launch_assign_f16(const ZView& z, const float* E, const float* ee, const voi
                                                              lblocks, p.wide, p.wide_count, p.wide_cap);
         VQ_LAUNCH_CHECK("vq_rerank_finish_kernel(list)");
       }
-      if (with_wide) {
+      if (with_wide && p.wide_buckets) {
+        const int per_tile = max(1, (sm_count() * 6) / p.NT);
+        vq_rerank_wide_tile_kernel<<<p.NT * per_tile, 256, 0, stream>>>(zq, E4, ee, K, p.NT, idx, p.cand2, p.cand3,
+                                                                         reinterpret_cast<const int32_t*>(p.wide), p.wide_count, p.wide_cap);
+        VQ_LAUNCH_CHECK("vq_rerank_wide_tile_kernel");
+      } else if (with_wide) {
         vq_rerank_finish_kernel<<<wfull, 256, 0, stream>>>(zq, E4, ee, K, idx, p.cand2, p.cand3, p.rr_list, p.rr_count,
                                                            0, p.wide, p.wide_count, p.wide_cap);
         VQ_LAUNCH_CHECK("vq_rerank_finish_kernel(wide)");
