@@ -529,9 +529,17 @@ __device__ __forceinline__ int resolve_group(const unsigned char* abuf, int row,
                                              int grp, float inv_sx, float thr_r) {
   __half2 xh[D / 2];
   const __half2 down = __float2half2_rn(0.000244140625f);       // 2^-12
+  // Every lane walks the 8 16-byte chunks of a row in its own order, chunk k = sg ^ j at step j.  The code rows a warp
+  // reads in one step are rows 4 g + c of 32 different groups g: (row & 7) takes only TWO values, so with the natural
+  // order all 32 lanes hit two 16-byte bank groups (16-way conflict: the 40 loads per row were ~60 % of this function's
+  // time).  sg = (row & 7) times x in GF(8): both sg and sg ^ (row & 7) are permutations of 0..7 over 8 consecutive
+  // rows, so the lanes of a quarter-warp spread over all bank groups for the code rows (at most 2-way) AND for their
+  // own rows (conflict-free).  The sum over chunks is order-independent within the error bound.
+  const int r7 = row & 7;
+  const int sg = ((r7 << 1) & 7) ^ ((r7 & 4) ? 3 : 0);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const uint4 h = *reinterpret_cast<const uint4*>(abuf + row * 128 + ((j ^ (row & 7)) << 4));
+    const uint4 h = *reinterpret_cast<const uint4*>(abuf + row * 128 + ((((sg ^ j)) ^ r7) << 4));
     const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) xh[4 * j + e] = __hmul2(*reinterpret_cast<const __half2*>(&hw[e]), down);
@@ -547,7 +555,7 @@ __device__ __forceinline__ int resolve_group(const unsigned char* abuf, int row,
     float acc = 0.f, acc1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const uint4 h = *reinterpret_cast<const uint4*>(er + ((j ^ (r & 7)) << 4));
+      const uint4 h = *reinterpret_cast<const uint4*>(er + (((sg ^ j) ^ (r & 7)) << 4));
       const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
       __half2 a2 = __hmul2(xh[4 * j], *reinterpret_cast<const __half2*>(&hw[0]));
 #pragma unroll
