@@ -535,8 +535,10 @@ __device__ __forceinline__ int resolve_group(const unsigned char* abuf, int row,
   // time).  sg = (row & 7) times x in GF(8): both sg and sg ^ (row & 7) are permutations of 0..7 over 8 consecutive
   // rows, so the lanes of a quarter-warp spread over all bank groups for the code rows (at most 2-way) AND for their
   // own rows (conflict-free).  The sum over chunks is order-independent within the error bound.
+  // (The code rows are 4 g + c: bit 2 of the row index is the parity of the group; folding it into the lane's order makes
+  // the code-row slot sg ^ j ^ c, the same permutation for every lane of the warp whatever its group.)
   const int r7 = row & 7;
-  const int sg = ((r7 << 1) & 7) ^ ((r7 & 4) ? 3 : 0);
+  const int sg = ((r7 << 1) & 7) ^ ((r7 & 4) ? 3 : 0) ^ ((grp & 1) << 2);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const uint4 h = *reinterpret_cast<const uint4*>(abuf + row * 128 + ((((sg ^ j)) ^ r7) << 4));
