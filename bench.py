@@ -90,9 +90,13 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def count_between(self, t0, t1):
+        return sum(1 for t, _ in self.lines if t0 <= t <= t1)
+
+    def stop(self, t0=None, t1=None, window=None):
+        """Summary of the samples received between t0 and t1 (host clock; all samples when omitted)."""
         if self.proc is None:
             return None
         time.sleep(0.15)
@@ -103,7 +107,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if t0 is not None and not (t0 <= ts <= t1):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -117,7 +123,10 @@ class ClockSampler:
         if not sm:
             return None
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        if window:
+            out["window"] = window
+        return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -360,6 +369,9 @@ def run_gpu(args):
         torch.autograd.backward([q, loss], [g, one])
         return loss, met
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                      # before the warm-up: nvidia-smi needs ~0.1 s before its first line
     zr = z.requires_grad_(True)
     for _ in range(args.warmup):
         step(zr)
@@ -371,10 +383,8 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
+    t_host0 = time.time()
     l0 = vqb200._lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -384,7 +394,25 @@ def run_gpu(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = vqb200._lib.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    t_host1 = time.time()
+    # clocks DURING the timed region; when that region is shorter than a few sampling periods (multi-GPU shards: 5 steps
+    # of 3.4 ms), every rank keeps running the same step until rank 0 has seen samples under the same load
+    need_more = 1 if (rank == 0 and sampler.count_between(t_host0, t_host1 + 0.02) < 2) else 0
+    if world > 1:
+        import torch.distributed as dist
+        nm = torch.tensor([need_more], device=dev)
+        dist.broadcast(nm, src=0)
+        need_more = int(nm.item())
+    clock_window = None
+    if need_more:
+        t_more0 = time.time()
+        n_more = max(1, int(0.5 / max(ms / args.steps * 1e-3, 1e-4)))
+        for _ in range(n_more):
+            step(zr)
+        barrier()
+        t_host0, t_host1 = t_more0, time.time()
+        clock_window = f"{n_more} more steps of the same workload right after the timed region (it was shorter than two sampling periods)"
+    clocks = sampler.stop(t_host0, t_host1 + 0.02, clock_window) if rank == 0 else None
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms], device=dev)
