@@ -1167,15 +1167,29 @@ vq_rerank_wide_tile_kernel(ZView z, const float4* __restrict__ E4, const float* 
   __syncthreads();
   float* xrow = X + warp * D;
   const float4* xs = reinterpret_cast<const float4*>(xrow);
-  for (int w = sub * 8 + warp; w < count; w += nsub * 8) {
-    const long long n = wide_rows[(size_t)tile * wide_cap + w];
+  // software pipeline over the warp's rows: the next row (64 scattered 4-byte reads = one DRAM round trip) and the
+  // row's other candidate groups are requested before the current row's 140 codes are evaluated
+  const int w0 = sub * 8 + warp, wstep = nsub * 8;
+  long long n_next = (w0 < count) ? wide_rows[(size_t)tile * wide_cap + w0] : 0;
+  float p0 = 0.f, p1 = 0.f;
+  if (w0 < count) {
+    const float* src = z.p + z.row_base(n_next);
+    p0 = __ldg(src + (long long)lane * z.sC);
+    p1 = __ldg(src + (long long)(lane + 32) * z.sC);
+  }
+  for (int w = w0; w < count; w += wstep) {
+    const long long n = n_next;
     __syncwarp();
-    {
-      const float* src = z.p + z.row_base(n);
-      xrow[lane] = __ldg(src + (long long)lane * z.sC);
-      xrow[lane + 32] = __ldg(src + (long long)(lane + 32) * z.sC);
+    xrow[lane] = p0; xrow[lane + 32] = p1;
+    __syncwarp();
+    int cg = -1;                                                   // lanes of groups 0..2: the row's candidate group g
+    if (g < 3) cg = (g == 0) ? (int)((uint32_t)idx[n] & ((1u << KIND_SHIFT) - 1)) : (g == 1) ? __ldg(cand2 + n) : __ldg(cand3 + n);
+    if (w + wstep < count) {
+      n_next = wide_rows[(size_t)tile * wide_cap + w + wstep];
+      const float* src = z.p + z.row_base(n_next);
+      p0 = __ldg(src + (long long)lane * z.sC);
+      p1 = __ldg(src + (long long)(lane + 32) * z.sC);
     }
-    __syncwarp();
     const float xx = row_sq(xs);
     float best = INFINITY; int bidx = INT_MAX;
 #pragma unroll 1
@@ -1195,10 +1209,7 @@ vq_rerank_wide_tile_kernel(ZView z, const float4* __restrict__ E4, const float* 
         if (cand_better(d, code, best, bidx)) { best = d; bidx = code; }
       }
     }
-    if (g < 3) {
-      const int grp = (g == 0) ? (int)((uint32_t)idx[n] & ((1u << KIND_SHIFT) - 1)) : (g == 1) ? __ldg(cand2 + n) : __ldg(cand3 + n);
-      if (grp * 4 + c < K) exact_code_e4s(xs, xx, E4, ee, grp, c, best, bidx);
-    }
+    if (g < 3 && cg * 4 + c < K) exact_code_e4s(xs, xx, E4, ee, cg, c, best, bidx);
     __syncwarp();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
