@@ -69,6 +69,9 @@ namespace vqb200 {
 int launch_assign_simt(const ZView& z, const float* E, const float* ee, int K, int D,
                        int32_t* idx, float* best, const int32_t* row_list, const int32_t* row_count,
                        long long max_rows, cudaStream_t stream, unsigned long long* keys = nullptr);
+int launch_assign_simt_capped(const ZView& z, const float* E, const float* ee, int K, int D,
+                              int32_t* idx, float* best, const int32_t* row_list, const int32_t* row_count,
+                              long long max_rows, cudaStream_t stream, unsigned long long* keys, long long key_cap);
 
 // VQB200_K1_DEBUG (compile time): knock-out knobs and clock64 stamps inside the hot loops (tools/f16_stamps.py and the
 // knock-out table in DESIGN.md were measured with it); the production build keeps only the launch-level knobs.
@@ -1258,9 +1261,10 @@ static long long f16_wide_cap(long long N) { return N / 8 + 64; }
 static size_t f16_n2(long long N) { return ((size_t)(N > 0 ? N : 0) + 1) & ~(size_t)1; }      // per-row arrays keep 8-byte alignment
 static size_t f16_ints(long long N) { return 64 + 4 * f16_n2(N) + (size_t)f16::RES_MAX_NT * (size_t)f16_wide_cap(N > 0 ? N : 0); }
 static size_t f16_keys_offset(long long N) { return (f16_ints(N) * sizeof(int32_t) + 7) & ~(size_t)7; }
+// merge keys of the exact kernel: one per LISTED row, at most F16_SPLIT_MAX_ROWS of them (longer lists are swept unsplit)
 size_t assign_f16_workspace_bytes(long long N) {
-  return (N > 0 && N <= F16_SPLIT_MAX_ROWS) ? f16_keys_offset(N) + (size_t)N * sizeof(unsigned long long)
-                                             : f16_ints(N) * sizeof(int32_t);
+  return (N > 0) ? f16_keys_offset(N) + (size_t)min(N, F16_SPLIT_MAX_ROWS) * sizeof(unsigned long long)
+                 : f16_ints(N) * sizeof(int32_t);
 }
 
 bool assign_f16_can_fuse_residual(const ZView& z, const float* r_out) {
@@ -1397,11 +1401,11 @@ int launch_assign_f16(const ZView& z, const float* E, const float* ee, const voi
     }
   }
   // exact re-do of the rows the filter could not prove (count lives on the device; no host sync)
-  unsigned long long* keys = (z.N <= F16_SPLIT_MAX_ROWS)
-      ? reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(workspace) + f16_keys_offset(z.N)) : nullptr;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(workspace) + f16_keys_offset(z.N));
   if (r_out) VQ_CHECK_ARG(p.stage_mode != STG_DIRECT, VQB200_EUNSUPPORTED, "vq_assign(TC): fused residual needs a contiguous layout");
   if (p.dbg & 32) return VQB200_OK;
-  return launch_assign_simt(zq, E, ee, K, D, idx, best, p.list, p.list_count, z.N, stream, keys);
+  return launch_assign_simt_capped(zq, E, ee, K, D, idx, best, p.list, p.list_count, z.N, stream, keys,
+                                   min(z.N, F16_SPLIT_MAX_ROWS));
 }
 
 }  // namespace vqb200

@@ -27,8 +27,9 @@ constexpr int LDE = BN + 4;
 
 __global__ void __launch_bounds__(256)
 assign_keys_finalize_kernel(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ row_list,
-                            const int32_t* __restrict__ row_count, int32_t* __restrict__ idx_out) {
+                            const int32_t* __restrict__ row_count, int32_t* __restrict__ idx_out, long long key_cap) {
   const int total = *row_count;
+  if (total > key_cap) return;                     // the sweep was not split (see vq_assign_simt_kernel)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
     idx_out[row_list[i]] = (int32_t)(keys[i] & 0xFFFFFFFFull);
 }
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(simt::NT, 2)
 vq_assign_simt_kernel(ZView z, const float* __restrict__ E, const float* __restrict__ ee,
                       int K, int D, int Dp, int32_t* __restrict__ idx_out, float* __restrict__ best_out,
                       const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count,
-                      int splits, unsigned long long* __restrict__ keys) {
+                      int splits_req, unsigned long long* __restrict__ keys_req, long long key_cap) {
   using namespace simt;
   extern __shared__ __align__(16) float smem[];
   float* zs = smem;                    // [Dp][LDZ]   k-major z tile
@@ -48,6 +49,10 @@ vq_assign_simt_kernel(ZView z, const float* __restrict__ E, const float* __restr
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const long long total = row_list ? (long long)(*row_count) : z.N;
+  // the merge keys are indexed by list position and there are only key_cap of them: a longer list (known only on the
+  // device) is swept unsplit, which is what a long list wants anyway
+  const int splits = (total <= key_cap) ? splits_req : 1;
+  unsigned long long* keys = (splits > 1) ? keys_req : nullptr;
   const long long ntiles = (total + BM - 1) / BM;
   const bool vecE = ((D & 3) == 0) && ((reinterpret_cast<uintptr_t>(E) & 15) == 0);
 
@@ -182,9 +187,10 @@ size_t assign_simt_smem_bytes(int D) {
 }
 
 // row_list == nullptr: all rows of the view.  Otherwise *row_count rows listed in row_list.
-int launch_assign_simt(const ZView& z, const float* E, const float* ee, int K, int D,
-                       int32_t* idx, float* best, const int32_t* row_list, const int32_t* row_count,
-                       long long max_rows, cudaStream_t stream, unsigned long long* keys) {
+// keys: key_cap 64-bit merge keys (or null): lists of up to key_cap rows are swept split over the codes.
+int launch_assign_simt_capped(const ZView& z, const float* E, const float* ee, int K, int D,
+                              int32_t* idx, float* best, const int32_t* row_list, const int32_t* row_count,
+                              long long max_rows, cudaStream_t stream, unsigned long long* keys, long long key_cap) {
   using namespace simt;
   const size_t smem = assign_simt_smem_bytes(D);
   VQ_CHECK_ARG(smem <= 227 * 1024, VQB200_ESHAPE, "vq_assign(SIMT): D=%d needs %zu B of shared memory (max 232448)", D, smem);
@@ -198,20 +204,27 @@ int launch_assign_simt(const ZView& z, const float* E, const float* ee, int K, i
   const long long tiles = (max_rows + BM - 1) / BM;
   // split the codebook sweep when the caller provides the merge keys (short work lists, see the header comment)
   int splits = 1;
-  if (keys && row_list && !best) {
+  if (keys && row_list && !best && key_cap > 0) {
     while (splits < 8 && (K / (splits * 2)) >= BN && (K % (splits * 2 * BN)) == 0) splits *= 2;
   }
-  if (splits > 1) VQ_CUDA(cudaMemsetAsync(keys, 0xFF, (size_t)max_rows * sizeof(unsigned long long), stream));
-  else keys = nullptr;
+  key_cap = min(key_cap, max_rows);
+  if (splits > 1) VQ_CUDA(cudaMemsetAsync(keys, 0xFF, (size_t)key_cap * sizeof(unsigned long long), stream));
+  else { keys = nullptr; key_cap = 0; }
   const int grid = (int)max(1LL, min(tiles * splits, (long long)sm_count() * 2));
-  vq_assign_simt_kernel<<<grid, NT, smem, stream>>>(z, E, ee, K, D, Dp, idx, best, row_list, row_count, splits, keys);
+  vq_assign_simt_kernel<<<grid, NT, smem, stream>>>(z, E, ee, K, D, Dp, idx, best, row_list, row_count, splits, keys, key_cap);
   VQ_LAUNCH_CHECK("vq_assign_simt_kernel");
   if (splits > 1) {
-    assign_keys_finalize_kernel<<<(int)max(1LL, min((max_rows + 255) / 256, (long long)sm_count())), 256, 0, stream>>>(
-        keys, row_list, row_count, idx);
+    assign_keys_finalize_kernel<<<(int)max(1LL, min((key_cap + 255) / 256, (long long)sm_count())), 256, 0, stream>>>(
+        keys, row_list, row_count, idx, key_cap);
     VQ_LAUNCH_CHECK("assign_keys_finalize_kernel");
   }
   return VQB200_OK;
+}
+
+int launch_assign_simt(const ZView& z, const float* E, const float* ee, int K, int D,
+                       int32_t* idx, float* best, const int32_t* row_list, const int32_t* row_count,
+                       long long max_rows, cudaStream_t stream, unsigned long long* keys) {
+  return launch_assign_simt_capped(z, E, ee, K, D, idx, best, row_list, row_count, max_rows, stream, keys, max_rows);
 }
 
 }  // namespace vqb200
