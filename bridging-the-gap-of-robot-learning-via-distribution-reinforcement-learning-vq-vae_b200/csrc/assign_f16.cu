@@ -523,9 +523,10 @@ __device__ __forceinline__ void row_emit(const Params& p, const RowTrack& tr, bo
 // pre-scaled by 2^-12 so that nothing overflows), the 16 partial sums per code are added in fp32: at most
 // 2^-9 |x||E| of extra error, which thr_r carries.  If the best code leads the other three by more than thr_r it is
 // provably the exact arg min and the row needs no re-rank at all (~93 % of the rows).
-// two codes in flight (and two partial sums per code): 3.04 instead of 3.07 ms per 10 M x 1024; four: 3.09
+// all four codes in flight (and two partial sums per code).  With the bank conflicts of the loads gone: 2.77 ms per
+// 10 M x 1024 (one code at a time 2.82, two 2.87); before that fix two were best (3.04 vs 3.07 / 3.09)
 #ifndef RESOLVE_UNROLL
-#define RESOLVE_UNROLL 2
+#define RESOLVE_UNROLL 4
 #endif
 constexpr int RESOLVE_UNROLL_N = RESOLVE_UNROLL;
 __device__ __forceinline__ int resolve_group(const unsigned char* abuf, int row, const unsigned char* sCB, const float* sM,
